@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- SDF points/sec of the DISN hot path at the 256^3 grid (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--res 256] [--precision P]
+
+One "step" = one pass of the hot path over one synthetic 137x137 image: encode (resize + VGG-16 + folds)
+then the dense (res+1)^3 SDF grid (projection + multi-scale gather + two-stream MLP + /10).  With N GPUs the
+grid's z-slabs are sharded across ranks (strong scaling: total work fixed), every rank re-encodes the image,
+and the SDF slabs are gathered to rank 0 with NCCL inside the timed region.
+
+`value`  : device-resident throughput (image + camera already in HBM; CUDA events, max over ranks).
+`e2e`    : the same metric through the public host-buffer API (pinned host image in, host SDF grid out).
+`--impl reference`: the CPU oracle restating the reference's TF graph (TF itself is not installable here),
+           all host threads, reference loop structure (whole graph incl. VGG per chunk), on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_ALG = 2164480.0          # algorithmic FLOP per SDF point (SURVEY.md 8d / DESIGN.md)
+METRIC = "sdf_points_per_sec"
+UNIT = "points/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"],
+                    source="measured")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_points_per_sec(sdf_res: int, sample_points: int, repeats: int = 1):
+    """Oracle timed the way the reference runs (test/create_sdf.py:262-275): per chunk, the whole graph
+    including VGG.  Bounded sample: `sample_points` points of the first chunk; the encoder cost is scaled
+    by sample/chunk so the number is the steady-state rate of the reference's loop."""
+    import torch
+    from disn_b200 import synth
+    from oracle import disn_oracle as orc
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    W = synth.make_weights(seed=7, init="he")
+    imgs = synth.synthetic_images(1)
+    tm = synth.DEMO_TRANS_MAT
+    R, total, split, nsp = orc.chunking(sdf_res)
+    pts = orc.grid_points(synth.DEMO_SDF_PARAMS[0], R)[:sample_points][None]
+    n = pts.shape[1]
+    best = None
+    for _ in range(repeats + 1):     # first pass = warm-up
+        t0 = time.perf_counter()
+        enc = orc.encode(imgs, W, dtype=np.float32)
+        t1 = time.perf_counter()
+        orc.decode(enc, pts, pts, tm, W, dtype=np.float32)
+        t2 = time.perf_counter()
+        t_chunk = (t1 - t0) + (t2 - t1) * (nsp / n)          # one full chunk as the reference executes it
+        rate = nsp / t_chunk
+        best = rate if best is None else max(best, rate)
+    return best, ncores, "%d-point sample of chunk 0 of the res-%d grid, VGG re-run per chunk (%d chunks of %d)" % (
+        n, sdf_res, split, nsp), (t1 - t0), (t2 - t1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rates = []
+    for _ in range(max(1, args.steps)):
+        rate, cores, sample, t_enc, t_dec = cpu_reference_points_per_sec(args.res, args.cpu_sample, repeats=0)
+        rates.append(rate)
+    value = float(np.median(rates))
+    R = args.res + 1
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * R ** 3 / value,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "single 137x137 image, --sdf_res %d (%d^3 = %d points), twostream" % (args.res, R, R ** 3),
+                      "note": "PyTorch/NumPy CPU restatement of the TF graph (TF 1.x not installable); ms_per_step extrapolated from the sample"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from disn_b200 import synth
+    from disn_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    R = args.res + 1
+    total_pts = R ** 3
+    # z-slab of this rank (contiguous in the output array: x fastest, z slowest)
+    z_bounds = [(r * R) // world for r in range(world + 1)]
+    z0, z1 = z_bounds[rank], z_bounds[rank + 1]
+    max_planes = max(z_bounds[i + 1] - z_bounds[i] for i in range(world))
+
+    eng = Engine(device=local_rank, precision=args.precision, max_batch=1)
+    W = synth.make_weights(seed=7, init="he")
+    eng.load_weights(W)
+    del W
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+
+    img_host = torch.from_numpy(synth.synthetic_images(1)).pin_memory()
+    tm_host = torch.from_numpy(synth.DEMO_TRANS_MAT.copy()).pin_memory()
+    img_dev = img_host.to(dev)
+    tm_dev = tm_host.to(dev)
+    slab = torch.empty((max_planes, R, R), dtype=torch.float32, device=dev)
+    full = torch.empty((world * max_planes, R, R), dtype=torch.float32, device=dev) if world > 1 else slab
+    out_host = torch.empty((R, R, R), dtype=torch.float32).pin_memory() if rank == 0 else None
+    sp = synth.DEMO_SDF_PARAMS
+
+    def step_device():
+        eng.encode_device(img_dev.data_ptr(), 1, 137, 137, 3)
+        eng.eval_grid_device(sp, tm_dev.data_ptr(), args.res, z0, z1, slab.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(full, slab)
+
+    def step_e2e():
+        img_dev.copy_(img_host, non_blocking=True)
+        tm_dev.copy_(tm_host, non_blocking=True)
+        step_device()
+        if rank == 0:
+            if world == 1:
+                out_host.copy_(slab, non_blocking=True)
+            else:
+                for r in range(world):
+                    n = z_bounds[r + 1] - z_bounds[r]
+                    out_host[z_bounds[r]:z_bounds[r + 1]].copy_(full[r * max_planes:r * max_planes + n], non_blocking=True)
+        stream.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    ms_total = timed(step_device, args.steps)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = total_pts / (ms_step * 1e-3)
+
+    # kernel-only duration of the dominant kernel (fused point kernel) on this rank's slab
+    barrier()
+    ke0, ke1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kreps = max(1, min(args.steps, 5))
+    ke0.record(stream)
+    for _ in range(kreps):
+        eng.eval_grid_device(sp, tm_dev.data_ptr(), args.res, z0, z1, slab.data_ptr())
+    ke1.record(stream)
+    torch.cuda.synchronize(dev)
+    k_ms = ke0.elapsed_time(ke1) / kreps
+    slab_pts = (z1 - z0) * R * R
+
+    # end-to-end through the host-buffer path
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
+    e2e_value = total_pts / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = load_peaks()
+        achieved = slab_pts * F_ALG / (k_ms * 1e-3) / 1e12
+        peak = peaks["bf16_sustained"]
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16x3 (bf16 hi/lo split operands, 3 MMAs/product, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": "single 137x137 image, --sdf_res %d (%d^3 = %d points), twostream, encoder included per step"
+                                   % (args.res, R, total_pts),
+                       "precision": args.precision, "parallelism": "z-slab x%d" % world,
+                       "l2": "inputs larger than L2: each step streams 554 MB of VGG weights + writes %.0f MB of SDF" % (total_pts * 4 / 1e6)},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "kernel": "fused point kernel (%s)" % args.precision,
+                         "kernel_ms": k_ms, "flop_per_point": F_ALG,
+                         "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["source"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(img_host.numel() * 4 + tm_host.numel() * 4),
+                    "d2h_bytes_per_step": int(total_pts * 4), "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores, sample, t_enc, t_dec = cpu_reference_points_per_sec(args.res, args.cpu_sample, repeats=0)
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--precision", default=os.environ.get("DISN_PRECISION", "fp32"), choices=["fp32", "bf16x3"])
+    ap.add_argument("--cpu-sample", type=int, default=8192, dest="cpu_sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,344 @@
+// C ABI of the DISN B200 hot-path library (see include/disn_b200.h for the reference call sites).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace disn {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace disn
+
+using namespace disn;
+
+extern "C" {
+
+const char* disn_last_error(void) { return g_err.c_str(); }
+
+void disn_default_config(disn_config* cfg) {
+  if (!cfg) return;
+  cfg->device = 0;
+  cfg->img_h = 137; cfg->img_w = 137;
+  cfg->vgg_in = 224;
+  cfg->num_classes = 1024;
+  cfg->clamp_max = 136.0f;
+  cfg->sdf_weight = 10.0f;
+  cfg->tanh_out = 0;
+  cfg->precision = DISN_PREC_FP32;
+  cfg->max_batch = 1;
+}
+
+int disn_create(const disn_config* cfg, disn_ctx** out) {
+  DISN_REQUIRE(cfg && out, "null config/out");
+  DISN_REQUIRE(cfg->max_batch >= 1 && cfg->max_batch <= 8, "max_batch in [1,8]");
+  DISN_REQUIRE(cfg->img_h > 1 && cfg->img_w > 1 && cfg->num_classes % 4 == 0, "bad image/embedding size");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(std::string("no CUDA device: the DISN B200 path has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    return -1;
+  }
+  DISN_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device ordinal out of range");
+  DISN_CUDA_OK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  DISN_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error("this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+              std::to_string(prop.minor));
+    return -1;
+  }
+  disn_ctx* c = new disn_ctx();
+  c->cfg = *cfg;
+  DISN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  DISN_CUDA_OK(cudaMalloc(&c->d_tm, sizeof(float) * 12 * 8));
+  *out = c;
+  return 0;
+}
+
+void disn_destroy(disn_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  encoder_free(c);
+  for (auto& kv : c->weights) cudaFree(kv.second.ptr);
+  for (float* p : {c->d_pts, c->d_pts_rot, c->d_out, c->d_uv, c->d_tm, c->d_axes, c->tc_small})
+    if (p) cudaFree(p);
+  if (c->tc_weights) cudaFree(c->tc_weights);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int disn_set_stream(disn_ctx* c, void* cuda_stream) {
+  DISN_REQUIRE(c, "null ctx");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (cuda_stream) {
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+  } else {
+    DISN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  return 0;
+}
+
+int disn_synchronize(disn_ctx* c) {
+  DISN_REQUIRE(c, "null ctx");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int disn_set_precision(disn_ctx* c, int32_t precision) {
+  DISN_REQUIRE(c, "null ctx");
+  DISN_REQUIRE(precision == DISN_PREC_FP32 || precision == DISN_PREC_BF16X3, "unknown precision");
+  c->cfg.precision = precision;
+  return 0;
+}
+
+int64_t disn_launch_count(disn_ctx* c) { return c ? c->launches : 0; }
+
+int disn_load_weight(disn_ctx* c, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+  DISN_REQUIRE(c && name && data && shape && ndim >= 1 && ndim <= 4, "bad load_weight arguments");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  int64_t numel = 1;
+  std::vector<int64_t> shp(shape, shape + ndim);
+  for (int i = 0; i < ndim; ++i) { DISN_REQUIRE(shape[i] > 0, "non-positive dim"); numel *= shape[i]; }
+  DevTensor& t = c->weights[name];
+  if (t.numel != numel) {
+    if (t.ptr) cudaFree(t.ptr);
+    t.ptr = nullptr;
+    DISN_CUDA_OK(cudaMalloc(&t.ptr, numel * sizeof(float)));
+  }
+  t.shape = shp;
+  t.numel = numel;
+  DISN_CUDA_OK(cudaMemcpy(t.ptr, data, numel * sizeof(float), cudaMemcpyHostToDevice));
+  c->weights_dirty = true;
+  return 0;
+}
+
+static int check_shape(disn_ctx* c, const std::string& name, std::initializer_list<int64_t> want) {
+  auto it = c->weights.find(name);
+  DISN_REQUIRE(it != c->weights.end(), "missing variable " + name);
+  std::vector<int64_t> w(want);
+  // accept [1,1,Cin,Cout] or [Cin,Cout] for 1x1 convs
+  const auto& s = it->second.shape;
+  int64_t nw = 1, ns = 1;
+  for (auto v : w) nw *= v;
+  for (auto v : s) ns *= v;
+  DISN_REQUIRE(nw == ns && s.back() == w.back(), "variable " + name + " has the wrong shape");
+  return 0;
+}
+
+int disn_finalize_weights(disn_ctx* c) {
+  DISN_REQUIRE(c, "null ctx");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  const int nc = c->cfg.num_classes;
+  for (const char* sc : {"sdfprediction", "sdfprediction_imgfeat"}) {
+    std::string p(sc);
+    int64_t cat = (p == "sdfprediction") ? 512 + nc : 512 + kLocalFeat;
+    if (check_shape(c, p + "/fold1/conv1/weights", {3, 64})) return -2;
+    if (check_shape(c, p + "/fold1/conv2/weights", {64, 256})) return -2;
+    if (check_shape(c, p + "/fold1/conv3/weights", {256, 512})) return -2;
+    if (check_shape(c, p + "/fold2/conv1/weights", {cat, 512})) return -2;
+    if (check_shape(c, p + "/fold2/conv2/weights", {512, 256})) return -2;
+    if (check_shape(c, p + "/fold2/conv5/weights", {256, 1})) return -2;
+    for (const char* l : {"fold1/conv1", "fold1/conv2", "fold1/conv3", "fold2/conv1", "fold2/conv2", "fold2/conv5"})
+      DISN_REQUIRE(c->weights.count(p + "/" + l + "/biases"), "missing variable " + p + "/" + l + "/biases");
+  }
+  if (tc_pack_weights(c)) return -1;
+  c->weights_dirty = false;
+  return 0;
+}
+
+int disn_encode(disn_ctx* c, const float* imgs, int32_t B, int32_t H, int32_t W, int32_t C, uint32_t flags) {
+  DISN_REQUIRE(c && imgs, "null ctx/imgs");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  DISN_REQUIRE(B <= c->cfg.max_batch, "batch exceeds max_batch of the context");
+  if (c->weights_dirty && disn_finalize_weights(c)) return -1;
+  if (encoder_run(c, imgs, B, H, W, C, (flags & DISN_DEVICE_PTR) != 0)) return -1;
+  if (!(flags & DISN_DEVICE_PTR)) DISN_CUDA_OK(cudaStreamSynchronize(c->stream));   // caller-owned host buffer
+  return 0;
+}
+
+int disn_get_encoded(disn_ctx* c, int32_t what, float* out, int64_t out_elems) {
+  DISN_REQUIRE(c && out, "null ctx/out");
+  DISN_REQUIRE(c->enc_B > 0, "disn_encode has not been called");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  static const int tapHW[5] = {224, 112, 56, 28, 14};
+  const float* src = nullptr;
+  int64_t n = 0, B = c->enc_B;
+  if (what == 0) { src = c->emb; n = B * c->cfg.num_classes; }
+  else if (what >= 1 && what <= 5) { src = c->taps[what - 1]; n = B * tapHW[what - 1] * tapHW[what - 1] * kTapC[what - 1]; }
+  else if (what == 6) { src = c->pmap; n = B * c->cfg.img_h * c->cfg.img_w * kHidden; }
+  else if (what == 7) { src = c->gbias; n = B * kHidden; }
+  else if (what == 8) { src = c->img_rs; n = B * c->cfg.vgg_in * c->cfg.vgg_in * 3; }
+  DISN_REQUIRE(src, "unknown `what`");
+  DISN_REQUIRE(out_elems == n, "output buffer has the wrong number of elements");
+  DISN_CUDA_OK(cudaMemcpyAsync(out, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static const float* W(disn_ctx* c, const std::string& n) { return c->weights.at(n).ptr; }
+
+static void fill_stream(disn_ctx* c, const std::string& p, StreamWeights& s) {
+  s.w1 = W(c, p + "/fold1/conv1/weights"); s.b1 = W(c, p + "/fold1/conv1/biases");
+  s.w2 = W(c, p + "/fold1/conv2/weights"); s.b2 = W(c, p + "/fold1/conv2/biases");
+  s.w3 = W(c, p + "/fold1/conv3/weights"); s.b3 = W(c, p + "/fold1/conv3/biases");
+  s.w4 = W(c, p + "/fold2/conv1/weights"); s.b4 = W(c, p + "/fold2/conv1/biases");
+  s.w5 = W(c, p + "/fold2/conv2/weights"); s.b5 = W(c, p + "/fold2/conv2/biases");
+  s.w6 = W(c, p + "/fold2/conv5/weights"); s.b6 = W(c, p + "/fold2/conv5/biases");
+}
+
+static int ensure_scratch(disn_ctx* c, int64_t pts) {
+  if (pts <= c->scratch_pts) return 0;
+  for (float** p : {&c->d_pts, &c->d_pts_rot, &c->d_out, &c->d_uv}) { if (*p) cudaFree(*p); *p = nullptr; }
+  DISN_CUDA_OK(cudaMalloc(&c->d_pts, pts * 3 * sizeof(float)));
+  DISN_CUDA_OK(cudaMalloc(&c->d_pts_rot, pts * 3 * sizeof(float)));
+  DISN_CUDA_OK(cudaMalloc(&c->d_out, pts * sizeof(float)));
+  DISN_CUDA_OK(cudaMalloc(&c->d_uv, pts * 2 * sizeof(float)));
+  c->scratch_pts = pts;
+  return 0;
+}
+
+static int run_job(disn_ctx* c, PointJob& job) {
+  job.gbias = c->gbias;
+  job.pmap = c->pmap;
+  job.img_h = c->cfg.img_h; job.img_w = c->cfg.img_w;
+  job.clamp_max = c->cfg.clamp_max;
+  job.tanh_out = c->cfg.tanh_out;
+  fill_stream(c, "sdfprediction", job.g);
+  fill_stream(c, "sdfprediction_imgfeat", job.l);
+  if (c->cfg.precision == DISN_PREC_BF16X3) return launch_point_tc(c, job);
+  return launch_point_fp32(c, job);
+}
+
+int disn_eval_points(disn_ctx* c, const float* pts, const float* pts_rot, const float* trans_mat, int32_t B,
+                     int64_t N, float* out_pred, float* out_uv, uint32_t flags) {
+  DISN_REQUIRE(c && pts && trans_mat && out_pred, "null argument");
+  DISN_REQUIRE(c->enc_B > 0, "disn_encode has not been called");
+  DISN_REQUIRE(B == c->enc_B, "batch differs from the encoded batch");
+  DISN_REQUIRE(N >= 0, "negative N");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (N == 0) return 0;
+  PointJob job{};
+  job.B = B; job.N = N; job.out_scale = 1.0f;
+  if (flags & DISN_DEVICE_PTR) {
+    job.pts = pts; job.pts_rot = (pts_rot && pts_rot != pts) ? pts_rot : nullptr;
+    job.trans_mat = trans_mat; job.out_pred = out_pred; job.out_uv = out_uv;
+    return run_job(c, job);
+  }
+  if (ensure_scratch(c, (int64_t)B * N)) return -1;
+  size_t nb = (size_t)B * N * 3 * sizeof(float);
+  DISN_CUDA_OK(cudaMemcpyAsync(c->d_pts, pts, nb, cudaMemcpyHostToDevice, c->stream));
+  job.pts = c->d_pts;
+  if (pts_rot && pts_rot != pts) {
+    DISN_CUDA_OK(cudaMemcpyAsync(c->d_pts_rot, pts_rot, nb, cudaMemcpyHostToDevice, c->stream));
+    job.pts_rot = c->d_pts_rot;
+  }
+  DISN_CUDA_OK(cudaMemcpyAsync(c->d_tm, trans_mat, (size_t)B * 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  job.trans_mat = c->d_tm;
+  job.out_pred = c->d_out;
+  job.out_uv = out_uv ? c->d_uv : nullptr;
+  if (run_job(c, job)) return -1;
+  DISN_CUDA_OK(cudaMemcpyAsync(out_pred, c->d_out, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (out_uv)
+    DISN_CUDA_OK(cudaMemcpyAsync(out_uv, c->d_uv, (size_t)B * N * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// numpy.linspace(start, stop, num) in float64, then cast to float32 (test/create_sdf.py:247-254):
+// y[i] = start + i*step with step = (stop-start)/(num-1), last element forced to stop.
+static void linspace_f32(double start, double stop, int num, float* out) {
+  if (num == 1) { out[0] = (float)start; return; }
+  const double div = (double)(num - 1);
+  const double delta = stop - start;
+  volatile double step = delta / div;
+  for (int i = 0; i < num; ++i) {
+    volatile double prod = (double)i * step;   // volatile: no FMA contraction, match numpy's two roundings
+    out[i] = (float)(prod + start);
+  }
+  out[num - 1] = (float)stop;
+}
+
+int disn_eval_grid(disn_ctx* c, const double* sdf_params, const float* trans_mat, int32_t B, int32_t sdf_res,
+                   int32_t z0, int32_t z1, float* out_sdf, uint32_t flags) {
+  DISN_REQUIRE(c && sdf_params && trans_mat && out_sdf, "null argument");
+  DISN_REQUIRE(c->enc_B > 0, "disn_encode has not been called");
+  DISN_REQUIRE(B == c->enc_B, "batch differs from the encoded batch");
+  DISN_REQUIRE(sdf_res >= 1, "sdf_res >= 1");
+  const int R = sdf_res + 1;
+  DISN_REQUIRE(z0 >= 0 && z1 <= R && z0 <= z1, "z range outside [0, sdf_res+1]");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  const int64_t N = (int64_t)(z1 - z0) * R * R;
+  if (N == 0) return 0;
+  // axis tables (host float64 linspace -> float32), uploaded per call: B*3*R floats
+  if (c->axes_R < R) {
+    if (c->d_axes) cudaFree(c->d_axes);
+    c->d_axes = nullptr;
+    DISN_CUDA_OK(cudaMalloc(&c->d_axes, (size_t)8 * 3 * R * sizeof(float)));
+    c->axes_R = R;
+  }
+  std::vector<float> axes((size_t)B * 3 * R);
+  for (int b = 0; b < B; ++b)
+    for (int a = 0; a < 3; ++a)
+      linspace_f32(sdf_params[b * 6 + a], sdf_params[b * 6 + 3 + a], R, &axes[((size_t)b * 3 + a) * R]);
+  DISN_CUDA_OK(cudaMemcpyAsync(c->d_axes, axes.data(), axes.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));   // `axes` is a stack-owned staging buffer
+
+  PointJob job{};
+  job.B = B; job.N = N; job.R = R; job.z0 = z0; job.axes = c->d_axes;
+  job.out_scale = 1.0f / c->cfg.sdf_weight;
+  if (flags & DISN_DEVICE_PTR) {
+    job.trans_mat = trans_mat;
+    job.out_pred = out_sdf;
+    return run_job(c, job);
+  }
+  if (ensure_scratch(c, (int64_t)B * N)) return -1;
+  DISN_CUDA_OK(cudaMemcpyAsync(c->d_tm, trans_mat, (size_t)B * 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  job.trans_mat = c->d_tm;
+  job.out_pred = c->d_out;
+  if (run_job(c, job)) return -1;
+  DISN_CUDA_OK(cudaMemcpyAsync(out_sdf, c->d_out, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int disn_write_dist(const char* path, int32_t res, const double* bbox, const float* values) {
+  DISN_REQUIRE(path && bbox && values && res >= 1, "bad write_dist arguments");
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error(std::string("cannot open ") + path); return -3; }
+  int32_t hdr[3] = {-res, res, res};
+  const size_t n = (size_t)(res + 1) * (res + 1) * (res + 1);
+  bool ok = fwrite(hdr, sizeof(int32_t), 3, f) == 3 && fwrite(bbox, sizeof(double), 6, f) == 6 &&
+            fwrite(values, sizeof(float), n, f) == n;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { set_error(std::string("short write to ") + path); return -3; }
+  return 0;
+}
+
+int disn_marching_cubes(disn_ctx* c, const float* sdf, int32_t R, const double* bbox, float iso, float* verts,
+                        int64_t* n_verts, int32_t* faces, int64_t* n_faces, uint32_t flags) {
+  DISN_REQUIRE(c && sdf && bbox && n_verts && n_faces, "null argument");
+  DISN_REQUIRE(R >= 2, "need at least 2 samples per axis");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  const float* d_sdf = sdf;
+  float* tmp = nullptr;
+  if (!(flags & DISN_DEVICE_PTR)) {
+    size_t nb = (size_t)R * R * R * sizeof(float);
+    DISN_CUDA_OK(cudaMalloc(&tmp, nb));
+    DISN_CUDA_OK(cudaMemcpyAsync(tmp, sdf, nb, cudaMemcpyHostToDevice, c->stream));
+    d_sdf = tmp;
+  }
+  int rc = marching_cubes(c, d_sdf, R, bbox, iso, verts, n_verts, faces, n_faces, verts == nullptr || faces == nullptr);
+  cudaStreamSynchronize(c->stream);
+  if (tmp) cudaFree(tmp);
+  return rc;
+}
+
+}  // extern "C"

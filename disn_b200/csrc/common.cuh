@@ -1,0 +1,131 @@
+// Shared declarations for the DISN B200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/disn_b200.h"
+
+namespace disn {
+
+void set_error(const std::string& msg);
+
+#define DISN_CUDA_OK(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::disn::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                        __FILE__ + ":" + std::to_string(__LINE__));                          \
+      return -1;                                                                             \
+    }                                                                                        \
+  } while (0)
+
+#define DISN_REQUIRE(cond, msg)                          \
+  do {                                                   \
+    if (!(cond)) {                                       \
+      ::disn::set_error(std::string("invalid argument: ") + (msg)); \
+      return -2;                                         \
+    }                                                    \
+  } while (0)
+
+struct DevTensor {
+  float* ptr = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+// VGG-16 topology (reference spec: models/CNN/vgg.py:187-196)
+static const int kNumConv = 13;
+static const int kTapLayer[5] = {1, 3, 6, 9, 12};  // conv1_2, conv2_2, conv3_3, conv4_3, conv5_3
+static const int kTapC[5] = {64, 128, 256, 512, 512};
+static const int kLocalFeat = 1472;
+static const int kHidden = 512;
+
+// One stream of the point MLP (models/sdfnet.py:69-92 / :171-190) after the algebraic folds.
+struct StreamWeights {
+  const float* w1; const float* b1;   // fold1/conv1 [3,64]
+  const float* w2; const float* b2;   // fold1/conv2 [64,256]
+  const float* w3; const float* b3;   // fold1/conv3 [256,512]
+  const float* w4;                    // fold2/conv1 rows 0..511 [512,512] (point-feature part)
+  const float* b4;                    // fold2/conv1 biases [512] (local stream; global uses gbias)
+  const float* w5; const float* b5;   // fold2/conv2 [512,256]
+  const float* w6; const float* b6;   // fold2/conv5 [256,1]
+};
+
+struct PointJob {
+  // inputs
+  const float* pts;       // [B,N,3] or nullptr (grid mode)
+  const float* pts_rot;   // [B,N,3] or nullptr (= pts)
+  const float* trans_mat; // [B,4,3] device
+  const float* axes;      // grid mode: [B,3,R] float32 linspace tables (x,y,z)
+  int32_t R;              // grid mode: points per axis
+  int32_t z0;             // grid mode: first z plane
+  int64_t N;              // points per image in this call
+  int32_t B;
+  // per-image encoder products
+  const float* gbias;     // [B,512]
+  const float* pmap;      // [B,img_h,img_w,512]
+  int32_t img_h, img_w;
+  float clamp_max;
+  float out_scale;        // 1 (eval_points) or 1/sdf_weight (eval_grid)
+  int32_t tanh_out;
+  StreamWeights g, l;
+  // outputs
+  float* out_pred;        // [B,N]
+  float* out_uv;          // [B,N,2] or nullptr
+};
+
+}  // namespace disn
+
+struct disn_ctx {
+  disn_config cfg;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::map<std::string, disn::DevTensor> weights;
+  bool weights_dirty = true;
+  int64_t launches = 0;
+
+  // encoder state
+  int32_t enc_B = 0;
+  int32_t alloc_B = 0;
+  float* img_in = nullptr;      // [B,H,W,3] as uploaded
+  float* img_rs = nullptr;      // [B,224,224,3]
+  float* act[2] = {nullptr, nullptr};   // ping-pong activations
+  float* taps[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* proj[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // per-level projected maps [B,h,h,512]
+  float* fc_a = nullptr;        // [B,4096]
+  float* fc_b = nullptr;        // [B,4096]
+  float* partial = nullptr;     // split-K partials
+  float* emb = nullptr;         // [B,num_classes]
+  float* gbias = nullptr;       // [B,512]
+  float* pmap = nullptr;        // [B,img_h,img_w,512]
+  float* w_local_feat = nullptr;   // view into fold2/conv1 weights rows 512.. [1472,512]
+  // scratch for host-pointer calls
+  float* d_pts = nullptr; float* d_pts_rot = nullptr; float* d_out = nullptr; float* d_uv = nullptr;
+  int64_t scratch_pts = 0;
+  float* d_tm = nullptr;        // [max_batch,4,3]
+  float* d_axes = nullptr;      // [max_batch,3,R]
+  int32_t axes_R = 0;
+  // bf16x3 packed weights (tcgen05 path)
+  void* tc_weights = nullptr;
+  int64_t tc_weights_bytes = 0;
+  float* tc_small = nullptr;    // fp32 small params for the tcgen05 kernel
+};
+
+namespace disn {
+// encoder.cu
+int encoder_alloc(disn_ctx* c, int B);
+int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool device_ptr);
+void encoder_free(disn_ctx* c);
+// point_fp32.cu
+int launch_point_fp32(disn_ctx* c, const PointJob& job);
+// point_tc.cu
+int tc_pack_weights(disn_ctx* c);
+int launch_point_tc(disn_ctx* c, const PointJob& job);
+// mc.cu
+int marching_cubes(disn_ctx* c, const float* d_sdf, int R, const double* bbox, float iso,
+                   float* verts, int64_t* n_verts, int32_t* faces, int64_t* n_faces, bool count_only);
+}  // namespace disn

@@ -1,0 +1,174 @@
+"""Python handle over the C-ABI context: one Engine = one CUDA device + one stream (not thread-safe)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DISN_DEVICE_PTR, PREC_BF16X3, PREC_FP32, DisnConfig, check
+
+_PREC = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3}
+TAP_HW = (224, 112, 56, 28, 14)
+TAP_C = (64, 128, 256, 512, 512)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Engine:
+    def __init__(self, device: int = 0, precision: str = "fp32", max_batch: int = 1, tanh: bool = False,
+                 img_h: int = 137, img_w: int = 137, num_classes: int = 1024, sdf_weight: float = 10.0):
+        self.lib = _lib.load()
+        cfg = DisnConfig()
+        self.lib.disn_default_config(C.byref(cfg))
+        cfg.device = device
+        cfg.precision = _PREC[precision]
+        cfg.max_batch = max_batch
+        cfg.tanh_out = int(bool(tanh))
+        cfg.img_h, cfg.img_w, cfg.num_classes = img_h, img_w, num_classes
+        cfg.sdf_weight = sdf_weight
+        cfg.clamp_max = float(img_h - 1)      # models/model_normalization.py:250 (136 for 137x137)
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        check(self.lib.disn_create(C.byref(cfg), C.byref(self._h)))
+        self.batch = 0
+
+    # -- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.disn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        check(self.lib.disn_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(self.lib.disn_synchronize(self._h))
+
+    def set_precision(self, precision: str):
+        check(self.lib.disn_set_precision(self._h, _PREC[precision]))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.disn_launch_count(self._h))
+
+    # -- weights ------------------------------------------------------------------------------
+    def load_weights(self, weights: dict):
+        """weights: TF variable name -> array (HWIO).  Unknown names are stored but unused."""
+        for name, arr in weights.items():
+            a = _f32(arr)
+            shp = (C.c_int64 * a.ndim)(*a.shape)
+            check(self.lib.disn_load_weight(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), shp, a.ndim))
+        check(self.lib.disn_finalize_weights(self._h))
+
+    # -- encoder ------------------------------------------------------------------------------
+    def encode(self, imgs):
+        a = _f32(imgs)
+        if a.ndim != 4:
+            raise ValueError("imgs must be [B,H,W,C]")
+        B, H, W, Cc = a.shape
+        check(self.lib.disn_encode(self._h, a.ctypes.data_as(C.c_void_p), B, H, W, Cc, 0))
+        self.batch = B
+
+    def encode_device(self, imgs_ptr: int, B: int, H: int, W: int, Cc: int = 3):
+        """Device-pointer, asynchronous variant."""
+        check(self.lib.disn_encode(self._h, C.c_void_p(imgs_ptr), B, H, W, Cc, DISN_DEVICE_PTR))
+        self.batch = B
+
+    def get_encoded(self, what: int) -> np.ndarray:
+        B = self.batch
+        cfg = self.cfg
+        if what == 0:
+            shape = (B, cfg.num_classes)
+        elif 1 <= what <= 5:
+            shape = (B, TAP_HW[what - 1], TAP_HW[what - 1], TAP_C[what - 1])
+        elif what == 6:
+            shape = (B, cfg.img_h, cfg.img_w, 512)
+        elif what == 7:
+            shape = (B, 512)
+        elif what == 8:
+            shape = (B, cfg.vgg_in, cfg.vgg_in, 3)
+        else:
+            raise ValueError(what)
+        out = np.empty(shape, dtype=np.float32)
+        check(self.lib.disn_get_encoded(self._h, what, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+    # -- points -------------------------------------------------------------------------------
+    def eval_points(self, pts, trans_mat, pts_rot=None, want_uv: bool = False):
+        """One `sess.run`: pts [B,N,3], trans_mat [B,4,3] -> pred_sdf [B,N,1] (and uv [B,N,2])."""
+        p = _f32(pts)
+        t = _f32(trans_mat)
+        B, N, _ = p.shape
+        pr = None if pts_rot is None else _f32(pts_rot)
+        out = np.empty((B, N, 1), dtype=np.float32)
+        uv = np.empty((B, N, 2), dtype=np.float32) if want_uv else None
+        check(self.lib.disn_eval_points(
+            self._h, p.ctypes.data_as(C.c_void_p), None if pr is None else pr.ctypes.data_as(C.c_void_p),
+            t.ctypes.data_as(C.c_void_p), B, N, out.ctypes.data_as(C.c_void_p),
+            None if uv is None else uv.ctypes.data_as(C.c_void_p), 0))
+        return (out, uv) if want_uv else out
+
+    def eval_points_device(self, pts_ptr: int, trans_mat_ptr: int, B: int, N: int, out_ptr: int,
+                           uv_ptr: int = 0, pts_rot_ptr: int = 0):
+        """Device-pointer, asynchronous variant (pointers from torch tensors' data_ptr())."""
+        check(self.lib.disn_eval_points(self._h, C.c_void_p(pts_ptr), C.c_void_p(pts_rot_ptr or 0),
+                                        C.c_void_p(trans_mat_ptr), B, N, C.c_void_p(out_ptr),
+                                        C.c_void_p(uv_ptr or 0), DISN_DEVICE_PTR))
+
+    def eval_grid(self, sdf_params, trans_mat, sdf_res: int, z0: int = 0, z1: int | None = None, out=None):
+        """Dense grid slab -> [B, z1-z0, R, R] float32 = pred/sdf_weight (reference `result`, reshaped)."""
+        sp = np.ascontiguousarray(sdf_params, dtype=np.float64).reshape(-1, 6)
+        t = _f32(trans_mat)
+        B = sp.shape[0]
+        R = sdf_res + 1
+        z1 = R if z1 is None else z1
+        if out is None:
+            out = np.empty((B, z1 - z0, R, R), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == B * (z1 - z0) * R * R
+        check(self.lib.disn_eval_grid(self._h, sp.ctypes.data_as(C.POINTER(C.c_double)),
+                                      t.ctypes.data_as(C.c_void_p), B, sdf_res, z0, z1,
+                                      out.ctypes.data_as(C.c_void_p), 0))
+        return out
+
+    def eval_grid_device(self, sdf_params, trans_mat_ptr: int, sdf_res: int, z0: int, z1: int, out_ptr: int):
+        sp = np.ascontiguousarray(sdf_params, dtype=np.float64).reshape(-1, 6)
+        check(self.lib.disn_eval_grid(self._h, sp.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(trans_mat_ptr),
+                                      sp.shape[0], sdf_res, z0, z1, C.c_void_p(out_ptr), DISN_DEVICE_PTR))
+
+    # -- marching cubes -----------------------------------------------------------------------
+    def marching_cubes(self, sdf, bbox, iso: float = 0.0, device_ptr: int | None = None, R: int | None = None):
+        """sdf [R,R,R] (z,y,x) -> (verts [V,3] float32, faces [F,3] int32 0-based)."""
+        bb = (C.c_double * 6)(*[float(v) for v in bbox])
+        if device_ptr is None:
+            a = _f32(sdf)
+            R = a.shape[0]
+            assert a.shape == (R, R, R)
+            ptr, flags = a.ctypes.data_as(C.c_void_p), 0
+        else:
+            ptr, flags = C.c_void_p(device_ptr), DISN_DEVICE_PTR
+        nv, nf = C.c_int64(0), C.c_int64(0)
+        check(self.lib.disn_marching_cubes(self._h, ptr, R, bb, float(iso), None, C.byref(nv), None, C.byref(nf), flags))
+        verts = np.empty((nv.value, 3), dtype=np.float32)
+        faces = np.empty((nf.value, 3), dtype=np.int32)
+        if nv.value and nf.value:
+            check(self.lib.disn_marching_cubes(self._h, ptr, R, bb, float(iso), verts.ctypes.data_as(C.c_void_p),
+                                               C.byref(nv), faces.ctypes.data_as(C.c_void_p), C.byref(nf), flags))
+        return verts, faces
+
+
+def write_dist(path: str, res: int, bbox, values):
+    """C-ABI .dist writer (test/create_sdf.py:292-303 layout)."""
+    v = _f32(values).reshape(-1)
+    if v.size != (res + 1) ** 3:
+        raise ValueError("values must hold (res+1)^3 samples")
+    bb = (C.c_double * 6)(*[float(x) for x in bbox])
+    check(_lib.load().disn_write_dist(path.encode(), res, bb, v.ctypes.data_as(C.c_void_p)))

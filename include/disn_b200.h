@@ -1,0 +1,119 @@
+/*
+ * disn_b200.h -- C ABI of the B200-native DISN SDF-inference hot path.
+ *
+ * The reference has no FFI on this path (it is a Python-built TF-1.x graph); the entry points
+ * below are what a replacement of that graph binds, one per reference call site
+ * (paths relative to the reference repo):
+ *
+ *   disn_create / disn_destroy      <-> tf.Session + model.get_model graph build
+ *                                       (test/create_sdf.py:152-176, models/model_normalization.py:47)
+ *   disn_load_weight                <-> tf.train.Saver.restore by variable name (test/create_sdf.py:180-192);
+ *                                       names/shapes = SURVEY.md 8a "checkpoint variable names"
+ *   disn_encode                     <-> image resize + vgg_16 + 5 tap resizes
+ *                                       (models/model_normalization.py:65-77,171-183; models/CNN/vgg.py:182-218)
+ *   disn_eval_points                <-> one sess.run([pred_sdf, ref_img, sample_img_points], feed_dict)
+ *                                       (test/create_sdf.py:262-275): get_img_points (:241-251), resampler x5,
+ *                                       sdfnet.get_sdf_basic2 (models/sdfnet.py:69-92),
+ *                                       sdfnet.get_sdf_basic2_imgfeat_twostream (:171-190), sum, optional tanh
+ *   disn_eval_grid                  <-> the whole chunk loop of test_one_epoch (test/create_sdf.py:241-285):
+ *                                       linspace/meshgrid grid, SPLIT_SIZE sess.runs, reassembly, /SDF_WEIGHT
+ *   disn_write_dist                 <-> to_binary (test/create_sdf.py:292-303)
+ *   disn_marching_cubes(+_to_obj)   <-> os.system("./isosurface/computeMarchingCubes <dist> <obj> -i <iso>")
+ *                                       (test/create_sdf.py:319-323)
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure with a thread-local message
+ * in disn_last_error(); the caller owns all buffers; all tensors are float32, row-major, NHWC / [B,N,C]
+ * exactly as the reference feeds them.  Pointers are HOST pointers unless DISN_DEVICE_PTR is set in
+ * `flags`, in which case points / trans_mat / outputs are device pointers on the context's device and
+ * the call is asynchronous on the context's stream.  One context = one CUDA device + one stream;
+ * a context is not thread-safe, distinct contexts are independent.
+ */
+#ifndef DISN_B200_H
+#define DISN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct disn_ctx disn_ctx;
+
+enum {
+  DISN_DEVICE_PTR = 1,   /* data pointers are device pointers; call is async on the ctx stream */
+};
+
+/* arithmetic used by the fused point kernel */
+enum {
+  DISN_PREC_FP32 = 0,    /* CUDA-core fp32 FMA (exact restatement of the reference arithmetic) */
+  DISN_PREC_BF16X3 = 1,  /* tcgen05 tensor cores, bf16 hi/lo split operands, 3 MMAs per product, fp32 accumulate */
+};
+
+typedef struct disn_config {
+  int32_t device;        /* CUDA device ordinal */
+  int32_t img_h, img_w;  /* FLAGS.img_h / img_w (137): size the feature taps are resized to */
+  int32_t vgg_in;        /* get_model img_size (224) */
+  int32_t num_classes;   /* FLAGS.num_classes (1024): width of the global embedding */
+  float clamp_max;       /* 136.0: upper clamp of projected pixel coordinates */
+  float sdf_weight;      /* SDF_WEIGHT (10.0): eval_grid divides by it */
+  int32_t tanh_out;      /* FLAGS.tanh */
+  int32_t precision;     /* DISN_PREC_* */
+  int32_t max_batch;     /* images per encode call the context pre-allocates for (>=1) */
+} disn_config;
+
+void disn_default_config(disn_config* cfg);
+
+int disn_create(const disn_config* cfg, disn_ctx** out);
+void disn_destroy(disn_ctx* ctx);
+const char* disn_last_error(void);
+
+/* Run the ctx on an externally owned CUDA stream (cudaStream_t passed as void*). NULL = own stream. */
+int disn_set_stream(disn_ctx* ctx, void* cuda_stream);
+int disn_synchronize(disn_ctx* ctx);
+int disn_set_precision(disn_ctx* ctx, int32_t precision);
+
+/* Weights by TF variable name, HWIO layout as TF stores them. Host pointer. Missing variables keep
+ * their previous value (zero on a fresh context), mirroring the reference's tolerant restore. */
+int disn_load_weight(disn_ctx* ctx, const char* name, const float* data, const int64_t* shape, int32_t ndim);
+/* Re-derive the packed / split forms the kernels read (call after the last disn_load_weight). */
+int disn_finalize_weights(disn_ctx* ctx);
+
+/* imgs: [B,H,W,C] (C = 3; H,W = 137 or vgg_in), host pointer (synchronous) or, with DISN_DEVICE_PTR,
+ * device pointer (asynchronous on the ctx stream). Keeps per-image features on the device. */
+int disn_encode(disn_ctx* ctx, const float* imgs, int32_t B, int32_t H, int32_t W, int32_t C, uint32_t flags);
+/* Fetch encoder products to host (tests / get_model end_points).
+ * what: 0 = img_embedding [B,num_classes]; 1..5 = raw VGG tap conv{1_2,2_2,3_3,4_3,5_3} [B,h,h,C];
+ *       6 = projected local map [B,img_h,img_w,512]; 7 = global-stream folded bias [B,512];
+ *       8 = resized input image [B,vgg_in,vgg_in,3]. */
+int disn_get_encoded(disn_ctx* ctx, int32_t what, float* out, int64_t out_elems);
+
+/* One sess.run: pts[B,N,3] (projection input, `sample_pc`), pts_rot[B,N,3] (MLP input, `sample_pc_rot`;
+ * NULL = same as pts), trans_mat[B,4,3] -> out_pred[B,N,1] (=pred_sdf, NOT divided by sdf_weight),
+ * out_uv[B,N,2] (=sample_img_points) or NULL. B must equal the last disn_encode batch. */
+int disn_eval_points(disn_ctx* ctx, const float* pts, const float* pts_rot, const float* trans_mat,
+                     int32_t B, int64_t N, float* out_pred, float* out_uv, uint32_t flags);
+
+/* Dense grid: sdf_params host double[B,6] = [xmin,ymin,zmin,xmax,ymax,zmax], trans_mat [B,4,3],
+ * resolution R = sdf_res+1 points per axis, z-planes [z0,z1) -> out_sdf[B,(z1-z0),R,R] = pred/sdf_weight
+ * (x fastest, z slowest, i.e. the reference's reassembled `result`). Grid coordinates are generated on
+ * the device from float64 linspace tables cast to float32, bit-identical to the reference's host grid. */
+int disn_eval_grid(disn_ctx* ctx, const double* sdf_params, const float* trans_mat, int32_t B,
+                   int32_t sdf_res, int32_t z0, int32_t z1, float* out_sdf, uint32_t flags);
+
+/* .dist writer: int32 {-res,res,res}, double bbox[6], float32 values[(res+1)^3]. Host values. */
+int disn_write_dist(const char* path, int32_t res, const double* bbox, const float* values);
+
+/* Marching cubes of sdf[R,R,R] (z,y,x) at iso over bbox. Two-call protocol: pass verts=faces=NULL to
+ * get counts, then call again with buffers of n_verts*3 floats / n_faces*3 int32 (0-based).
+ * sdf is a host pointer unless DISN_DEVICE_PTR. Vertices are welded (shared per grid edge) and ordered
+ * by (z,y,x,axis) of their edge; faces by cell index. */
+int disn_marching_cubes(disn_ctx* ctx, const float* sdf, int32_t R, const double* bbox, float iso,
+                        float* verts, int64_t* n_verts, int32_t* faces, int64_t* n_faces, uint32_t flags);
+
+/* Kernel launch counter (bench's gpu_launches): number of this library's kernels launched so far. */
+int64_t disn_launch_count(disn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISN_B200_H */

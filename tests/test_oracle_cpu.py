@@ -1,0 +1,97 @@
+"""CPU tests: the oracle against the golden fixtures and its own internal consistency."""
+import os
+import tempfile
+
+import numpy as np
+
+from disn_b200 import synth
+from oracle import disn_oracle as orc
+
+
+def test_chunking_matches_reference_expressions(golden):
+    for sdf_res, R, total, split, nsp in golden["chunking"]["table"]:
+        assert orc.chunking(int(sdf_res)) == (R, total, split, nsp)
+    # known answers of the driver arithmetic
+    assert orc.chunking(64) == (65, 274625, 2, 137313)
+    assert orc.chunking(128) == (129, 2146689, 10, 214669)
+    assert orc.chunking(256) == (257, 16974593, 80, 212183)
+    assert orc.chunking(512) == (513, 135005697, 629, 214636)
+
+
+def test_cameras_match_reference_preprocessing(golden):
+    cam = golden["cameras"]
+    for p, ref in zip(cam["params"], cam["trans_mat"]):
+        mine = synth.make_trans_mat(p[0], p[1], p[2], p[3], p[4:7])
+        np.testing.assert_allclose(mine, ref, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(synth.intrinsics(), cam["K"][0], atol=0)
+    # cam_est/model_cam.py:28
+    np.testing.assert_array_equal(synth.intrinsics(), [[149.84375, 0, 68.5], [0, 149.84375, 68.5], [0, 0, 1]])
+    # demo constant reproduced from the commented cam_gt
+    assert np.abs(cam["trans_mat"][0] - synth.DEMO_TRANS_MAT[0]).max() < 1e-5
+
+
+def test_dist_writer_matches_reference_reader(golden):
+    g = golden["dist_roundtrip"]
+    res = int(g["res"])
+    with tempfile.TemporaryDirectory() as td:
+        fn = os.path.join(td, "o.dist")
+        orc.to_binary(res, list(g["bbox"]), g["values"].astype(np.float64), fn)
+        assert np.array_equal(np.fromfile(fn, dtype=np.uint8), g["file_bytes"])
+
+
+def test_oracle_regression_pin(golden, he_weights):
+    g = golden["oracle_small"]
+    imgs = synth.synthetic_images(1)
+    out = orc.get_model(imgs, g["pts"], g["pts"], synth.DEMO_TRANS_MAT, he_weights, dtype=np.float32)
+    np.testing.assert_allclose(out["pred_sdf"], g["pred32"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(out["sample_img_points"], g["uv"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(out["img_embedding"], g["emb32"], rtol=1e-4, atol=1e-5)
+    # the synthetic He-scaled weights give O(1) predictions, so a 1e-4 bar on pred/10 is not vacuous
+    assert 0.3 < float(np.sqrt(np.mean(g["pred64"] ** 2))) < 3.0
+    assert np.abs(g["pred32"] - g["pred64"]).max() < 1e-4
+
+
+def test_folded_formulation_equals_graph(he_weights):
+    """The two algebraic folds the CUDA path uses are exact (checked in float64)."""
+    imgs = synth.synthetic_images(1, seed=77)
+    pts = np.random.default_rng(3).uniform(-1, 1, size=(1, 256, 3)).astype(np.float32)
+    tm = synth.synthetic_trans_mats(1)
+    enc = orc.encode(imgs, he_weights, dtype=np.float64)
+    ref = orc.decode(enc, pts, pts, tm, he_weights, dtype=np.float64)["pred_sdf"]
+    fold = orc.folded_decode(enc, pts, tm, he_weights, dtype=np.float64)
+    assert np.abs(ref - fold).max() < 1e-9
+
+
+def test_tf_resize_semantics():
+    # legacy (no half-pixel) bilinear: out[i] samples in[i*scale]; last rows replicate the edge
+    x = np.arange(4, dtype=np.float32).reshape(1, 1, 4, 1)
+    y = orc.tf_resize_bilinear(x, 1, 8)[0, 0, :, 0]
+    np.testing.assert_allclose(y, [0, 0.5, 1, 1.5, 2, 2.5, 3, 3])
+    # identity when sizes match
+    r = np.random.default_rng(0).random((2, 5, 7, 3), dtype=np.float32)
+    np.testing.assert_array_equal(orc.tf_resize_bilinear(r, 5, 7), r)
+
+
+def test_resampler_semantics():
+    data = np.arange(12, dtype=np.float32).reshape(1, 3, 4, 1)     # H=3, W=4
+    warp = np.array([[[0, 0], [1.5, 0.5], [3, 2], [3.5, 2], [-0.5, 0], [4.0, 1.0], [-1.0, 0.0]]], np.float32)
+    out = orc.tf_resampler(data, warp)[0, :, 0]
+    # (3.5,2): right taps fall outside -> contribute 0; (-0.5,0): left taps outside
+    np.testing.assert_allclose(out, [0, 3.5, 11, 5.5, 0, 0, 0])
+
+
+def test_grid_points_order_and_padding():
+    pts = orc.grid_points([-1, -1, -1, 1, 1, 1], 3)
+    assert pts.shape == (27, 3) and pts.dtype == np.float32
+    np.testing.assert_array_equal(pts[0], [-1, -1, -1])
+    np.testing.assert_array_equal(pts[1], [0, -1, -1])      # x fastest
+    np.testing.assert_array_equal(pts[3], [-1, 0, -1])
+    np.testing.assert_array_equal(pts[9], [-1, -1, 0])      # z slowest
+
+
+def test_get_loss_metrics():
+    pred = np.array([[[1.0], [-2.0], [0.5]]], np.float32)
+    gt = np.array([[[0.1], [-0.1], [-0.05]]], np.float32)
+    m = orc.get_loss(pred, gt)
+    assert abs(m["accuracy"] - 2 / 3) < 1e-6
+    assert abs(m["sdf_loss_realvalue"] - np.mean([0.0, 0.1, 0.1])) < 1e-6
