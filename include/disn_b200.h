@@ -110,6 +110,10 @@ int disn_write_dist(const char* path, int32_t res, const double* bbox, const flo
 int disn_marching_cubes(disn_ctx* ctx, const float* sdf, int32_t R, const double* bbox, float iso,
                         float* verts, int64_t* n_verts, int32_t* faces, int64_t* n_faces, uint32_t flags);
 
+/* Diagnostic: one CTA-pair tcgen05 (cta_group::2) GEMM D[128x256] = A[128x64] * B[256x64]^T, `passes` times
+ * accumulated; returns the raw TMEM image D_out[2 CTAs][128 lanes][128 columns]. Host pointers. */
+int disn_tc_selftest(int device, const float* A, const float* B, int passes, float* D_out);
+
 /* Kernel launch counter (bench's gpu_launches): number of this library's kernels launched so far. */
 int64_t disn_launch_count(disn_ctx* ctx);
 
