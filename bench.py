@@ -164,7 +164,11 @@ def run_ours(args):
     W = synth.make_weights(seed=7, init="he")
     eng.load_weights(W)
     del W
-    stream = torch.cuda.current_stream(dev)
+    # an explicit (non-default) stream: torch's default stream has handle 0, which the C ABI reads as
+    # "use the context's own stream" -- events must be recorded on the stream the kernels run on
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
 
     img_host = torch.from_numpy(synth.synthetic_images(1)).pin_memory()

@@ -283,13 +283,20 @@ int disn_eval_grid(disn_ctx* c, const double* sdf_params, const float* trans_mat
     c->d_axes = nullptr;
     DISN_CUDA_OK(cudaMalloc(&c->d_axes, (size_t)8 * 3 * R * sizeof(float)));
     c->axes_R = R;
+    c->axes_key.clear();
   }
-  std::vector<float> axes((size_t)B * 3 * R);
-  for (int b = 0; b < B; ++b)
-    for (int a = 0; a < 3; ++a)
-      linspace_f32(sdf_params[b * 6 + a], sdf_params[b * 6 + 3 + a], R, &axes[((size_t)b * 3 + a) * R]);
-  DISN_CUDA_OK(cudaMemcpyAsync(c->d_axes, axes.data(), axes.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));   // `axes` is a stack-owned staging buffer
+  // re-upload only when the boxes / resolution change (keeps repeated calls free of host syncs)
+  std::vector<double> key(sdf_params, sdf_params + (size_t)B * 6);
+  key.push_back((double)R);
+  if (key != c->axes_key) {
+    std::vector<float> axes((size_t)B * 3 * R);
+    for (int b = 0; b < B; ++b)
+      for (int a = 0; a < 3; ++a)
+        linspace_f32(sdf_params[b * 6 + a], sdf_params[b * 6 + 3 + a], R, &axes[((size_t)b * 3 + a) * R]);
+    DISN_CUDA_OK(cudaMemcpyAsync(c->d_axes, axes.data(), axes.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    DISN_CUDA_OK(cudaStreamSynchronize(c->stream));   // `axes` is a stack-owned staging buffer
+    c->axes_key = key;
+  }
 
   PointJob job{};
   job.B = B; job.N = N; job.R = R; job.z0 = z0; job.axes = c->d_axes;

@@ -109,6 +109,7 @@ struct disn_ctx {
   float* d_tm = nullptr;        // [max_batch,4,3]
   float* d_axes = nullptr;      // [max_batch,3,R]
   int32_t axes_R = 0;
+  std::vector<double> axes_key; // (sdf_params, R) the tables in d_axes were built from
   // bf16x3 packed weights (tcgen05 path)
   void* tc_weights = nullptr;
   int64_t tc_weights_bytes = 0;

@@ -1,9 +1,505 @@
-// tcgen05 (bf16x3) fused point kernel -- placeholder until the tensor-core path lands.
+// Fused per-point SDF kernel on tcgen05 tensor cores (DISN_PREC_BF16X3), sm_100a.
+//
+// Same math as point_fp32.cu (projection -> gather of the folded feature map -> two point-MLP streams
+// -> sum; models/model_normalization.py:241-251,169-206, models/sdfnet.py:69-92,171-190), but the four
+// wide layers of each stream run on the 5th-gen tensor cores.  To hold the reference's 1e-4 bar every
+// fp32 operand is split x = hi + lo (two bf16) and each product is three MMAs (hi*hi + lo*hi + hi*lo)
+// accumulated in fp32 in TMEM (error ~2^-17 per operand instead of bf16's 2^-9).
+//
+// Organisation (one CTA pair = one cluster of 2, cta_group::2, UMMA M=128 x N=256 x K=16):
+//   * a pair-tile is 128 query points, 64 per CTA (the 2x2 datapath keeps a 512-wide fp32 layer output
+//     for 64 points in 256 TMEM columns, so one layer's input and output accumulators fit in TMEM);
+//   * activations never leave the SM: layer l's accumulator is drained 32 columns at a time by the
+//     epilogue warps (bias / folded image features, ReLU, bf16 hi/lo split) into a 3-slot ring of
+//     K-major 128B-swizzled A tiles that layer l+1's MMAs consume (K-outer), so MMA and epilogue pipeline;
+//   * weights are pre-split, pre-permuted and pre-swizzled on the host into the exact 16 KB shared-memory
+//     images the B operand needs and streamed by the bulk-copy engine (cp.async.bulk) through an 8-stage
+//     mbarrier ring; each CTA loads only its half of every B tile;
+//   * warp roles: 0 weight producer, 1 MMA issuer (leader CTA) / full-barrier relay (peer CTA),
+//     2 TMEM allocator, 4-7 epilogue (one TMEM lane each), 8-11 front end (points, projection, layer 1,
+//     bilinear gather of the projected feature map into a shared-memory ring).
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace disn {
-int tc_pack_weights(disn_ctx*) { return 0; }
-int launch_point_tc(disn_ctx*, const PointJob&) {
-  set_error("DISN_PREC_BF16X3 path is not built in this revision");
-  return -4;
+namespace {
+
+constexpr int NW = 8;                 // weight ring stages
+constexpr int NX = 3;                 // activation (A operand) ring slots
+constexpr int NG = 2;                 // gather ring slots
+constexpr int W_STAGE = 16384;        // 128 rows x 64 k x bf16
+constexpr int X_HALF = 8192;          // 64 rows x 64 k x bf16
+constexpr int G_LD = 65;              // padded point stride of the gather ring
+constexpr int PTS = 64;               // points per CTA per tile
+constexpr int NTHREADS = 384;
+constexpr int STAGES_PER_STREAM = 66; // 2 + 16 + 32 + 16 weight stages (pair-level, 32 KB each)
+constexpr int XSLOTS_PER_STREAM = 21; // 1 + 4 + 8 + 8 activation slices
+
+struct TcSmem {
+  alignas(1024) uint8_t w[NW][W_STAGE];
+  alignas(1024) uint8_t x[NX][2][X_HALF];      // [slot][hi|lo]
+  float g[NG][64 * G_LD];                      // gathered image features [h*32+j][point]
+  float px[PTS], py[PTS], pz[PTS];
+  int tap_off[PTS][4];
+  float tap_w[PTS][4];
+  float part[2][2][2][PTS];                    // [tile parity][stream][half][point]
+  alignas(8) uint64_t wfull[NW];
+  uint64_t wpeer[NW];
+  uint64_t wempty[NW];
+  uint64_t xfull[NX];
+  uint64_t xempty[NX];
+  uint64_t gfull[NG];
+  uint64_t gempty[NG];
+  uint64_t acc_full[4];
+  uint64_t acc5_free;
+  uint32_t tmem_base;
+};
+
+// feature index held by (half h, thread-column c) of an accumulator (2x2 datapath, N=256 per MMA)
+__host__ __device__ constexpr int fout(int h, int c) { return (c / 128) * 256 + h * 128 + (c % 128); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+struct TileCoord { int b; int64_t n0; };
+__device__ __forceinline__ TileCoord tile_coord(int64_t tile, int64_t tiles_per_img) {
+  TileCoord t;
+  t.b = (int)(tile / tiles_per_img);
+  t.n0 = (tile % tiles_per_img) * (2 * PTS);
+  return t;
+}
+
+// write one thread's 32 consecutive K values (hi and lo) of row p into an A-tile slot
+__device__ __forceinline__ void store_slice(uint8_t* xhi, uint8_t* xlo, int p, int h, const float* v) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) tc::split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t off = tc::sw128_offset((uint32_t)p, (uint32_t)(h * 4 + q));
+    *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+    *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per_img) {
+  extern __shared__ uint8_t smem_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const uint32_t cta = tc::cluster_ctarank();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int num_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int64_t total_tiles = tiles_per_img * job.B;
+  const int my_tiles = (pair < total_tiles) ? (int)((total_tiles - pair + num_pairs - 1) / num_pairs) : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < NW; ++i) { tc::mbar_init(&s.wfull[i], 1); tc::mbar_init(&s.wpeer[i], 1); tc::mbar_init(&s.wempty[i], 1); }
+    for (int i = 0; i < NX; ++i) { tc::mbar_init(&s.xfull[i], 8); tc::mbar_init(&s.xempty[i], 1); }
+    for (int i = 0; i < NG; ++i) { tc::mbar_init(&s.gfull[i], 4); tc::mbar_init(&s.gempty[i], 4); }
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&s.acc_full[i], 1);
+    tc::mbar_init(&s.acc5_free, 8);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc_cg2(&s.tmem_base, 512);
+    tc::tmem_relinquish_cg2();
+  }
+  tc::tc_fence_before_sync();
+  tc::cluster_sync();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== weight producer (bulk-copy engine) =====================
+    if (lane == 0) {
+      uint32_t seq = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int g = 0; g < 2 * STAGES_PER_STREAM; ++g, ++seq) {
+          const int st = seq % NW;
+          tc::mbar_wait(&s.wempty[st], ((seq / NW) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&s.wfull[st], W_STAGE);
+          tc::bulk_g2s(s.w[st], wpk + (size_t)g * (2 * W_STAGE) + (size_t)cta * W_STAGE, W_STAGE, &s.wfull[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta == 1) {
+      // ===================== relay: peer's weight stages are resident =====================
+      if (lane == 0) {
+        uint32_t seq = 0;
+        for (int it = 0; it < my_tiles; ++it)
+          for (int g = 0; g < 2 * STAGES_PER_STREAM; ++g, ++seq) {
+            const int st = seq % NW;
+            tc::mbar_wait(&s.wfull[st], (seq / NW) & 1);
+            tc::mbar_arrive_cluster(&s.wpeer[st], 0);
+          }
+      }
+    } else if (lane == 0) {
+      // ===================== MMA issuer (leader CTA, one thread) =====================
+      const uint32_t idesc = tc::make_idesc_bf16(128, 256);
+      uint32_t wseq = 0, xseq = 0, nstream = 0;
+      auto wait_w = [&](uint32_t sq) -> uint64_t {
+        const int st = sq % NW;
+        const uint32_t ph = (sq / NW) & 1;
+        tc::mbar_wait(&s.wfull[st], ph);
+        tc::mbar_wait_cluster(&s.wpeer[st], ph);
+        tc::tc_fence_after_sync();
+        return tc::make_desc_sw128(tc::smem_u32(s.w[st]));
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int sidx = 0; sidx < 2; ++sidx, ++nstream) {
+#pragma unroll 1
+          for (int layer = 0; layer < 4; ++layer) {
+            const int nsl = (layer == 0) ? 1 : (layer == 1 ? 4 : 8);
+            const int nnb = (layer == 1 || layer == 2) ? 2 : 1;
+            const uint32_t colbase = (layer & 1) ? 256u : 0u;
+            if (layer == 1 && nstream > 0) {   // acc3 overwrites the columns the previous stream's acc5 used
+              tc::mbar_wait_cluster(&s.acc5_free, (nstream - 1) & 1);
+              tc::tc_fence_after_sync();
+            }
+#pragma unroll 1
+            for (int t = 0; t < nsl; ++t, ++xseq) {
+              const int slot = xseq % NX;
+              tc::mbar_wait_cluster(&s.xfull[slot], (xseq / NX) & 1);
+              tc::tc_fence_after_sync();
+              const uint64_t a_hi = tc::make_desc_sw128(tc::smem_u32(s.x[slot][0]));
+              const uint64_t a_lo = tc::make_desc_sw128(tc::smem_u32(s.x[slot][1]));
+#pragma unroll 1
+              for (int nb = 0; nb < nnb; ++nb) {
+                const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
+                uint64_t bdesc = wait_w(wseq);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc::mma_cg2(d, tc::desc_advance_k(a_hi, k * 16), tc::desc_advance_k(bdesc, k * 16), idesc,
+                              (t | k) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc::mma_cg2(d, tc::desc_advance_k(a_lo, k * 16), tc::desc_advance_k(bdesc, k * 16), idesc, 1u);
+                tc::commit_cg2(&s.wempty[wseq % NW], 0b11);
+                ++wseq;
+                bdesc = wait_w(wseq);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc::mma_cg2(d, tc::desc_advance_k(a_hi, k * 16), tc::desc_advance_k(bdesc, k * 16), idesc, 1u);
+                tc::commit_cg2(&s.wempty[wseq % NW], 0b11);
+                ++wseq;
+              }
+              tc::commit_cg2(&s.xempty[slot], 0b11);
+            }
+            tc::commit_cg2(&s.acc_full[layer], 0b11);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue: TMEM -> bias/ReLU/split -> A-tile ring =====================
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const int p = row & 63, h = row >> 6;
+    const uint32_t tlane = tmem + ((uint32_t)(ew * 32) << 16);
+    uint32_t gseq = 0;
+
+    auto arrive_xfull = [&](int slot) {
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta == 0) tc::mbar_arrive(&s.xfull[slot]);
+        else tc::mbar_arrive_cluster(&s.xfull[slot], 0);
+      }
+    };
+    // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into activation slice `seq`
+    auto drain = [&](uint32_t col0, int t, const float* __restrict__ bias, uint32_t seq, bool gather) {
+      const int slot = seq % NX;
+      tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
+      uint32_t r[32];
+      tc::tmem_ld_x32(tlane + col0 + 32u * t, r);
+      const int f0 = fout(h, 32 * t);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 bq = __ldg(reinterpret_cast<const float4*>(bias + f0 + j));
+        v[j] = bq.x; v[j + 1] = bq.y; v[j + 2] = bq.z; v[j + 3] = bq.w;
+      }
+      if (gather) {
+        const int gs = gseq % NG;
+        tc::mbar_wait(&s.gfull[gs], (gseq / NG) & 1);
+        const float* gp = s.g[gs] + (h * 32) * G_LD + p;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += gp[j * G_LD];
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s.gempty[gs]);
+        ++gseq;
+      }
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + v[j], 0.f);
+      store_slice(s.x[slot][0], s.x[slot][1], p, h, v);
+      arrive_xfull(slot);
+    };
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const TileCoord tc0 = tile_coord((int64_t)pair + (int64_t)it * num_pairs, tiles_per_img);
+      for (int sidx = 0; sidx < 2; ++sidx) {
+        const StreamWeights& w = sidx ? job.l : job.g;
+        const uint32_t seq0 = (uint32_t)it * (2 * XSLOTS_PER_STREAM) + sidx * XSLOTS_PER_STREAM;
+        const uint32_t par = (uint32_t)(it * 2 + sidx) & 1;
+        // fold1/conv2 output (256) -> X3
+        tc::mbar_wait(&s.acc_full[0], par);
+        tc::tc_fence_after_sync();
+        for (int t = 0; t < 4; ++t) drain(0u, t, w.b2, seq0 + 1 + t, false);
+        // fold1/conv3 output (512) -> X4
+        tc::mbar_wait(&s.acc_full[1], par);
+        tc::tc_fence_after_sync();
+        for (int t = 0; t < 8; ++t) drain(256u, t, w.b3, seq0 + 5 + t, false);
+        // fold2/conv1 output (512) + folded image features -> X5
+        tc::mbar_wait(&s.acc_full[2], par);
+        tc::tc_fence_after_sync();
+        const float* b4 = sidx ? w.b4 : (job.gbias + (int64_t)tc0.b * kHidden);
+        for (int t = 0; t < 8; ++t) drain(0u, t, b4, seq0 + 13 + t, sidx == 1);
+        // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
+        tc::mbar_wait(&s.acc_full[3], par);
+        tc::tc_fence_after_sync();
+        float part = 0.f;
+        for (int t = 0; t < 4; ++t) {
+          uint32_t r[32];
+          tc::tmem_ld_x32(tlane + 256u + 32u * t, r);
+          const int f0 = fout(h, 32 * t);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = fmaxf(__uint_as_float(r[j]) + __ldg(w.b5 + f0 + j), 0.f);
+            part = fmaf(a, __ldg(w.w6 + f0 + j), part);
+          }
+        }
+        tc::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (cta == 0) tc::mbar_arrive(&s.acc5_free);
+          else tc::mbar_arrive_cluster(&s.acc5_free, 0);
+        }
+        s.part[it & 1][sidx][h][p] = part;
+      }
+      named_bar_sync(1, 128);
+      if (h == 0) {
+        const int64_t n = tc0.n0 + (int64_t)cta * PTS + p;
+        if (n < job.N) {
+          const float (*pp)[2][PTS] = s.part[it & 1];
+          float rg = (pp[0][0][p] + pp[0][1][p]) + __ldg(job.g.b6);
+          float rl = (pp[1][0][p] + pp[1][1][p]) + __ldg(job.l.b6);
+          float r = rg + rl;
+          if (job.tanh_out) r = tanhf(r);
+          job.out_pred[(int64_t)tc0.b * job.N + n] = r * job.out_scale;
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== front end: points, projection, layer 1, feature gather =====================
+    const int ft = tid - 256;
+    const int p = ft & 63, h = ft >> 6;
+    const int fw = warp - 8;
+    const int Wm = job.img_w, Hm = job.img_h;
+
+    auto stage_x2 = [&](const StreamWeights& w, uint32_t seq) {
+      const int slot = seq % NX;
+      tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
+      const float x = s.px[p], y = s.py[p], z = s.pz[p];
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int f = h * 32 + j;
+        float a = __ldg(w.b1 + f);
+        a = fmaf(x, __ldg(w.w1 + f), a);
+        a = fmaf(y, __ldg(w.w1 + 64 + f), a);
+        a = fmaf(z, __ldg(w.w1 + 128 + f), a);
+        v[j] = fmaxf(a, 0.f);
+      }
+      store_slice(s.x[slot][0], s.x[slot][1], p, h, v);
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta == 0) tc::mbar_arrive(&s.xfull[slot]);
+        else tc::mbar_arrive_cluster(&s.xfull[slot], 0);
+      }
+    };
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const TileCoord tc0 = tile_coord((int64_t)pair + (int64_t)it * num_pairs, tiles_per_img);
+      const int b = tc0.b;
+      named_bar_sync(2, 128);
+      if (ft < PTS) {
+        const int64_t n = tc0.n0 + (int64_t)cta * PTS + ft;
+        float x = 0.f, y = 0.f, z = 0.f, xr = 0.f, yr = 0.f, zr = 0.f;
+        if (n < job.N) {
+          if (job.pts) {
+            const float* q = job.pts + ((int64_t)b * job.N + n) * 3;
+            x = q[0]; y = q[1]; z = q[2];
+            if (job.pts_rot) {
+              const float* r = job.pts_rot + ((int64_t)b * job.N + n) * 3;
+              xr = r[0]; yr = r[1]; zr = r[2];
+            } else { xr = x; yr = y; zr = z; }
+          } else {
+            const int R = job.R;
+            const int ix = (int)(n % R);
+            const int64_t tt = n / R;
+            const int iy = (int)(tt % R);
+            const int iz = (int)(tt / R) + job.z0;
+            const float* ax = job.axes + (int64_t)b * 3 * R;
+            x = ax[ix]; y = ax[R + iy]; z = ax[2 * R + iz];
+            xr = x; yr = y; zr = z;
+          }
+        }
+        const float* T = job.trans_mat + b * 12;
+        const float q0 = fmaf(z, T[6], fmaf(y, T[3], x * T[0])) + T[9];
+        const float q1 = fmaf(z, T[7], fmaf(y, T[4], x * T[1])) + T[10];
+        const float q2 = fmaf(z, T[8], fmaf(y, T[5], x * T[2])) + T[11];
+        const float u = fminf(job.clamp_max, fmaxf(0.f, q0 / q2));
+        const float v = fminf(job.clamp_max, fmaxf(0.f, q1 / q2));
+        s.px[ft] = xr; s.py[ft] = yr; s.pz[ft] = zr;
+        if (job.out_uv && n < job.N) {
+          float* o = job.out_uv + ((int64_t)b * job.N + n) * 2;
+          o[0] = u; o[1] = v;
+        }
+        // tf.contrib.resampler taps (zero outside the map, whole sample zero unless -1<x<W, -1<y<H)
+        int off[4] = {-1, -1, -1, -1};
+        float wg[4] = {0.f, 0.f, 0.f, 0.f};
+        if (u > -1.f && v > -1.f && u < (float)Wm && v < (float)Hm) {
+          const int fx = (int)floorf(u), fy = (int)floorf(v);
+          const int cx = fx + 1, cy = fy + 1;
+          const float dx = (float)cx - u, dy = (float)cy - v;
+          const int tx[4] = {fx, cx, fx, cx}, ty[4] = {fy, cy, cy, fy};
+          const float ww[4] = {dx * dy, (1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (tx[k] >= 0 && tx[k] < Wm && ty[k] >= 0 && ty[k] < Hm) {
+              off[k] = (ty[k] * Wm + tx[k]) * kHidden;
+              wg[k] = ww[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s.tap_off[ft][k] = off[k]; s.tap_w[ft][k] = wg[k]; }
+      }
+      named_bar_sync(2, 128);
+      stage_x2(job.g, (uint32_t)it * (2 * XSLOTS_PER_STREAM));
+      stage_x2(job.l, (uint32_t)it * (2 * XSLOTS_PER_STREAM) + XSLOTS_PER_STREAM);
+      // gather of the projected feature map for the local stream's fold2/conv1 epilogue
+      const float* pm = job.pmap + (int64_t)b * Hm * Wm * kHidden;
+      const int grp = lane >> 3, q = lane & 7;
+      for (int t = 0; t < 8; ++t) {
+        const uint32_t gsq = (uint32_t)it * 8 + t;
+        const int gs = gsq % NG;
+        tc::mbar_wait(&s.gempty[gs], ((gsq / NG) & 1) ^ 1);
+        float* gdst = s.g[gs];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pt = fw * 16 + i * 4 + grp;
+          int off[4];
+          float wg[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { off[k] = s.tap_off[pt][k]; wg[k] = s.tap_w[pt][k]; }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int fb = fout(hh, 32 * t) + q * 4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (off[k] >= 0) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(pm + off[k] + fb));
+                a.x = fmaf(wg[k], m.x, a.x); a.y = fmaf(wg[k], m.y, a.y);
+                a.z = fmaf(wg[k], m.z, a.z); a.w = fmaf(wg[k], m.w, a.w);
+              }
+            }
+            float* d = gdst + (hh * 32 + q * 4) * G_LD + pt;
+            d[0] = a.x; d[G_LD] = a.y; d[2 * G_LD] = a.z; d[3 * G_LD] = a.w;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s.gfull[gs]);
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc::tc_fence_before_sync();
+  tc::cluster_sync();
+  if (warp == 2) tc::tmem_dealloc_cg2(tmem, 512);
+}
+
+// K-slice t, position k (0..63) of a layer whose input activations have width `K` -> input feature index
+inline int fin_of(int layer, int t, int k) {
+  if (layer == 0) return k;                           // X2 is written in natural order
+  const int c = 32 * t + (k % 32);
+  return fout(k / 32, c);
+}
+
+}  // namespace
+
+// Pack both streams' tensor-core layers into the kernel's B-operand stage images:
+//   for stream, layer, slice t, N-block nb, part (hi, lo), CTA half c : 16 KB [128 rows n][64 k] SW128 bf16
+int tc_pack_weights(disn_ctx* c) {
+  static const int Ks[4] = {64, 256, 512, 512}, Ns[4] = {256, 512, 512, 256};
+  const size_t total = (size_t)2 * STAGES_PER_STREAM * 2 * W_STAGE;
+  std::vector<uint8_t> img(total, 0);
+  size_t stage = 0;
+  for (int sidx = 0; sidx < 2; ++sidx) {
+    const std::string p = sidx ? "sdfprediction_imgfeat" : "sdfprediction";
+    const char* names[4] = {"/fold1/conv2/weights", "/fold1/conv3/weights", "/fold2/conv1/weights", "/fold2/conv2/weights"};
+    for (int layer = 0; layer < 4; ++layer) {
+      auto it = c->weights.find(p + names[layer]);
+      DISN_REQUIRE(it != c->weights.end(), "missing variable " + p + names[layer]);
+      const int K = Ks[layer], N = Ns[layer];
+      std::vector<float> w((size_t)K * N);   // rows 0..K-1 of the [Cin,Cout] matrix (point-feature part)
+      DISN_CUDA_OK(cudaMemcpy(w.data(), it->second.ptr, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      for (int t = 0; t < K / 64; ++t)
+        for (int nb = 0; nb < N / 256; ++nb)
+          for (int part = 0; part < 2; ++part, ++stage)
+            for (int half = 0; half < 2; ++half) {
+              uint8_t* dst = img.data() + stage * (2 * W_STAGE) + (size_t)half * W_STAGE;
+              for (int nl = 0; nl < 128; ++nl) {
+                const int n = nb * 256 + half * 128 + nl;
+                for (int k = 0; k < 64; ++k) {
+                  const float v = w[(size_t)fin_of(layer, t, k) * N + n];
+                  const __nv_bfloat16 hi = __float2bfloat16(v);
+                  const __nv_bfloat16 out = part == 0 ? hi : __float2bfloat16(v - __bfloat162float(hi));
+                  memcpy(dst + tc::sw128_offset(nl, k / 8) + (k % 8) * 2, &out, 2);
+                }
+              }
+            }
+    }
+  }
+  DISN_REQUIRE(stage == (size_t)2 * STAGES_PER_STREAM, "internal: stage count");
+  if (c->tc_weights_bytes != (int64_t)total) {
+    if (c->tc_weights) cudaFree(c->tc_weights);
+    c->tc_weights = nullptr;
+    DISN_CUDA_OK(cudaMalloc(&c->tc_weights, total));
+    c->tc_weights_bytes = (int64_t)total;
+  }
+  DISN_CUDA_OK(cudaMemcpy(c->tc_weights, img.data(), total, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int launch_point_tc(disn_ctx* c, const PointJob& job) {
+  DISN_REQUIRE(c->tc_weights != nullptr, "tensor-core weights not packed (call disn_finalize_weights)");
+  static bool attr_set = false;
+  const int smem = (int)sizeof(TcSmem) + 1024;
+  if (!attr_set) {
+    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int64_t tiles_per_img = (job.N + 2 * PTS - 1) / (2 * PTS);
+  const int64_t total = tiles_per_img * job.B;
+  if (total == 0) return 0;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
+  int pairs = (int)std::min<int64_t>(total, sms / 2);
+  point_tc_kernel<<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(c->tc_weights),
+                                                           tiles_per_img);
+  c->launches++;
+  DISN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace disn

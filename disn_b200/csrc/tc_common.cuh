@@ -65,20 +65,29 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
-#ifndef DISN_MBAR_SPIN_LIMIT
-#define DISN_MBAR_SPIN_LIMIT (1u << 28)
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#ifndef DISN_MBAR_TIMEOUT_NS
+#define DISN_MBAR_TIMEOUT_NS 4000000000ull   // 4 s: far beyond any legitimate wait in these kernels
 #endif
-// Bounded spin: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > DISN_MBAR_SPIN_LIMIT) __trap();
+    if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > DISN_MBAR_TIMEOUT_NS) __trap();
   }
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > DISN_MBAR_SPIN_LIMIT) __trap();
+    if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > DISN_MBAR_TIMEOUT_NS) __trap();
   }
 }
 

@@ -33,3 +33,57 @@ def test_tcgen05_cta_pair_gemm_layout(passes):
             got[c * 64:(c + 1) * 64, h * 128:(h + 1) * 128] = D[c, h * 64:(h + 1) * 64, :]
     assert np.isfinite(got).all()
     assert np.abs(got - ref).max() < 1e-3 * np.abs(ref).max()
+
+
+@pytest.fixture(scope="module")
+def tc_engine(he_weights):
+    from disn_b200.engine import Engine
+    eng = Engine(device=0, precision="bf16x3", max_batch=2)
+    eng.load_weights(he_weights)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [1, 64, 127, 128, 129, 1000, 20000])
+def test_tc_eval_points_matches_oracle(tc_engine, he_weights, n):
+    """bf16x3 tensor-core path vs the fp64 oracle: |sdf - ref| <= 1e-4 (north_star tolerance)."""
+    from disn_b200 import synth
+    from oracle import disn_oracle as orc
+    imgs = synth.synthetic_images(2, seed=1234)
+    tc_engine.encode(imgs)
+    enc = orc.encode(imgs, he_weights, dtype=np.float64)
+    rng = np.random.default_rng(200 + n)
+    pts = rng.uniform(-1, 1, size=(2, n, 3)).astype(np.float32)
+    tm = np.concatenate([synth.DEMO_TRANS_MAT, synth.synthetic_trans_mats(1)], axis=0)
+    pred, uv = tc_engine.eval_points(pts, tm, want_uv=True)
+    nref = min(n, 3000)      # keep the CPU oracle in seconds
+    ref = orc.decode(enc, pts[:, :nref], pts[:, :nref], tm, he_weights, dtype=np.float64)
+    np.testing.assert_allclose(uv[:, :nref], ref["sample_img_points"], rtol=0, atol=2e-4)
+    err = np.abs(pred[:, :nref] - ref["pred_sdf"]).max() / orc.SDF_WEIGHT
+    assert err <= 1e-4, err
+    if n > nref:     # the rest against the fp32 CUDA-core path
+        tc_engine.set_precision("fp32")
+        p32 = tc_engine.eval_points(pts, tm)
+        tc_engine.set_precision("bf16x3")
+        assert np.abs(pred - p32).max() / orc.SDF_WEIGHT <= 1e-4
+
+
+def test_tc_grid_matches_fp32_path_and_slabs(tc_engine):
+    from disn_b200 import synth
+    from oracle import disn_oracle as orc
+    imgs = synth.synthetic_images(1, seed=5)
+    tc_engine.encode(imgs)
+    tm = synth.DEMO_TRANS_MAT
+    sp = np.array([[-1.0, -0.9, -0.8, 1.0, 0.7, 0.9]])
+    g_tc = tc_engine.eval_grid(sp, tm, 40)
+    tc_engine.set_precision("fp32")
+    g_32 = tc_engine.eval_grid(sp, tm, 40)
+    tc_engine.set_precision("bf16x3")
+    assert g_tc.shape == (1, 41, 41, 41)
+    err = np.abs(g_tc - g_32).max()
+    rms = np.sqrt(np.mean(g_32.astype(np.float64) ** 2))
+    assert err <= 1e-4, (err, rms)
+    assert rms > 0.02          # the field is O(0.1): the bar is not vacuous
+    a = tc_engine.eval_grid(sp, tm, 40, z0=0, z1=17)
+    b = tc_engine.eval_grid(sp, tm, 40, z0=17, z1=41)
+    np.testing.assert_array_equal(np.concatenate([a, b], axis=1), g_tc)   # deterministic, slab-invariant
