@@ -27,7 +27,7 @@
 namespace disn {
 namespace {
 
-constexpr int NW = 8;                 // weight ring stages
+constexpr int NW = 7;                 // weight ring stages
 constexpr int NX = 3;                 // activation (A operand) ring slots
 constexpr int NG = 2;                 // gather ring slots
 constexpr int W_STAGE = 16384;        // 128 rows x 64 k x bf16
@@ -36,11 +36,12 @@ constexpr int G_LD = 65;              // padded point stride of the gather ring
 constexpr int PTS = 64;               // points per CTA per tile
 constexpr int NTHREADS = 384;
 constexpr int STAGES_PER_STREAM = 66; // 2 + 16 + 32 + 16 weight stages (pair-level, 32 KB each)
-constexpr int XSLOTS_PER_STREAM = 21; // 1 + 4 + 8 + 8 activation slices
+constexpr int XSLOTS_PER_STREAM = 20; // 4 + 8 + 8 activation slices drained from TMEM (layer-1 output has its own slot)
 
 struct TcSmem {
   alignas(1024) uint8_t w[NW][W_STAGE];
-  alignas(1024) uint8_t x[NX][2][X_HALF];      // [slot][hi|lo]
+  alignas(1024) uint8_t x[NX][2][X_HALF];      // [slot][hi|lo]  ring written by the epilogue warps
+  alignas(1024) uint8_t x2[2][X_HALF];         // fold1/conv1 output (layer-2 A operand) written by the front end
   float g[NG][64 * G_LD];                      // gathered image features [h*32+j][point]
   float px[PTS], py[PTS], pz[PTS];
   int tap_off[PTS][4];
@@ -51,6 +52,8 @@ struct TcSmem {
   uint64_t wempty[NW];
   uint64_t xfull[NX];
   uint64_t xempty[NX];
+  uint64_t x2full;
+  uint64_t x2empty;
   uint64_t gfull[NG];
   uint64_t gempty[NG];
   uint64_t acc_full[4];
@@ -99,6 +102,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
   if (tid == 0) {
     for (int i = 0; i < NW; ++i) { tc::mbar_init(&s.wfull[i], 1); tc::mbar_init(&s.wpeer[i], 1); tc::mbar_init(&s.wempty[i], 1); }
     for (int i = 0; i < NX; ++i) { tc::mbar_init(&s.xfull[i], 8); tc::mbar_init(&s.xempty[i], 1); }
+    tc::mbar_init(&s.x2full, 8);
+    tc::mbar_init(&s.x2empty, 1);
     for (int i = 0; i < NG; ++i) { tc::mbar_init(&s.gfull[i], 4); tc::mbar_init(&s.gempty[i], 4); }
     for (int i = 0; i < 4; ++i) tc::mbar_init(&s.acc_full[i], 1);
     tc::mbar_init(&s.acc5_free, 8);
@@ -162,12 +167,20 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
               tc::tc_fence_after_sync();
             }
 #pragma unroll 1
-            for (int t = 0; t < nsl; ++t, ++xseq) {
+            for (int t = 0; t < nsl; ++t) {
               const int slot = xseq % NX;
-              tc::mbar_wait_cluster(&s.xfull[slot], (xseq / NX) & 1);
-              tc::tc_fence_after_sync();
-              const uint64_t a_hi = tc::make_desc_sw128(tc::smem_u32(s.x[slot][0]));
-              const uint64_t a_lo = tc::make_desc_sw128(tc::smem_u32(s.x[slot][1]));
+              uint64_t a_hi, a_lo;
+              if (layer == 0) {      // A operand = layer-1 output staged by the front end
+                tc::mbar_wait_cluster(&s.x2full, nstream & 1);
+                tc::tc_fence_after_sync();
+                a_hi = tc::make_desc_sw128(tc::smem_u32(s.x2[0]));
+                a_lo = tc::make_desc_sw128(tc::smem_u32(s.x2[1]));
+              } else {
+                tc::mbar_wait_cluster(&s.xfull[slot], (xseq / NX) & 1);
+                tc::tc_fence_after_sync();
+                a_hi = tc::make_desc_sw128(tc::smem_u32(s.x[slot][0]));
+                a_lo = tc::make_desc_sw128(tc::smem_u32(s.x[slot][1]));
+              }
 #pragma unroll 1
               for (int nb = 0; nb < nnb; ++nb) {
                 const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
@@ -188,7 +201,12 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                 tc::commit_cg2(&s.wempty[wseq % NW], 0b11);
                 ++wseq;
               }
-              tc::commit_cg2(&s.xempty[slot], 0b11);
+              if (layer == 0) {
+                tc::commit_cg2(&s.x2empty, 0b11);
+              } else {
+                tc::commit_cg2(&s.xempty[slot], 0b11);
+                ++xseq;
+              }
             }
             tc::commit_cg2(&s.acc_full[layer], 0b11);
           }
@@ -250,16 +268,16 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         // fold1/conv2 output (256) -> X3
         tc::mbar_wait(&s.acc_full[0], par);
         tc::tc_fence_after_sync();
-        for (int t = 0; t < 4; ++t) drain(0u, t, w.b2, seq0 + 1 + t, false);
+        for (int t = 0; t < 4; ++t) drain(0u, t, w.b2, seq0 + t, false);
         // fold1/conv3 output (512) -> X4
         tc::mbar_wait(&s.acc_full[1], par);
         tc::tc_fence_after_sync();
-        for (int t = 0; t < 8; ++t) drain(256u, t, w.b3, seq0 + 5 + t, false);
+        for (int t = 0; t < 8; ++t) drain(256u, t, w.b3, seq0 + 4 + t, false);
         // fold2/conv1 output (512) + folded image features -> X5
         tc::mbar_wait(&s.acc_full[2], par);
         tc::tc_fence_after_sync();
         const float* b4 = sidx ? w.b4 : (job.gbias + (int64_t)tc0.b * kHidden);
-        for (int t = 0; t < 8; ++t) drain(0u, t, b4, seq0 + 13 + t, sidx == 1);
+        for (int t = 0; t < 8; ++t) drain(0u, t, b4, seq0 + 12 + t, sidx == 1);
         // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
         tc::mbar_wait(&s.acc_full[3], par);
         tc::tc_fence_after_sync();
@@ -303,9 +321,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     const int fw = warp - 8;
     const int Wm = job.img_w, Hm = job.img_h;
 
-    auto stage_x2 = [&](const StreamWeights& w, uint32_t seq) {
-      const int slot = seq % NX;
-      tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
+    auto stage_x2 = [&](const StreamWeights& w, uint32_t use) {   // use = running stream count
+      tc::mbar_wait(&s.x2empty, (use & 1) ^ 1);
       const float x = s.px[p], y = s.py[p], z = s.pz[p];
       float v[32];
 #pragma unroll
@@ -317,12 +334,12 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         a = fmaf(z, __ldg(w.w1 + 128 + f), a);
         v[j] = fmaxf(a, 0.f);
       }
-      store_slice(s.x[slot][0], s.x[slot][1], p, h, v);
+      store_slice(s.x2[0], s.x2[1], p, h, v);
       tc::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (cta == 0) tc::mbar_arrive(&s.xfull[slot]);
-        else tc::mbar_arrive_cluster(&s.xfull[slot], 0);
+        if (cta == 0) tc::mbar_arrive(&s.x2full);
+        else tc::mbar_arrive_cluster(&s.x2full, 0);
       }
     };
 
@@ -383,8 +400,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         for (int k = 0; k < 4; ++k) { s.tap_off[ft][k] = off[k]; s.tap_w[ft][k] = wg[k]; }
       }
       named_bar_sync(2, 128);
-      stage_x2(job.g, (uint32_t)it * (2 * XSLOTS_PER_STREAM));
-      stage_x2(job.l, (uint32_t)it * (2 * XSLOTS_PER_STREAM) + XSLOTS_PER_STREAM);
+      stage_x2(job.g, (uint32_t)it * 2);
+      stage_x2(job.l, (uint32_t)it * 2 + 1);
       // gather of the projected feature map for the local stream's fold2/conv1 epilogue
       const float* pm = job.pmap + (int64_t)b * Hm * Wm * kHidden;
       const int grp = lane >> 3, q = lane & 7;

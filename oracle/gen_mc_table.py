@@ -93,9 +93,50 @@ def triangulate_case(case):
             seen.add(cur)
             cur = nxt[cur]
         assert len(loop) >= 3
-        for i in range(1, len(loop) - 1):      # loop order already gives normals towards the outside
-            tris.append((loop[0], loop[i], loop[i + 1]))
+        tris.extend(triangulate_loop(loop))    # loop order already gives normals towards the outside
     return tris
+
+
+FACE_EDGE_SETS = [frozenset(EDGE_OF[frozenset((q[k], q[(k + 1) % 4]))] for k in range(4)) for q in FACES]
+
+
+def coplanar(e1, e2):
+    return any(e1 in fs and e2 in fs for fs in FACE_EDGE_SETS)
+
+
+def all_triangulations(idx):
+    """all triangulations of the polygon idx[0..n-1] (indices into the loop), as lists of index triples"""
+    n = len(idx)
+    if n < 3:
+        return [[]]
+    if n == 3:
+        return [[tuple(idx)]]
+    out = []
+    for k in range(1, n - 1):                  # triangle (idx[0], idx[k], idx[n-1]) splits the polygon
+        for left in all_triangulations(idx[:k + 1]):
+            for right in all_triangulations(idx[k:]):
+                out.append(left + [(idx[0], idx[k], idx[n - 1])] + right)
+    return out
+
+
+def triangulate_loop(loop):
+    """Triangulate so that no diagonal lies in a cube face: a diagonal inside a face could coincide with a
+    diagonal of the neighbouring cube and make the mesh non-manifold.  Deterministic: first valid
+    triangulation in enumeration order (fans from the lowest edge id come first)."""
+    n = len(loop)
+    cands = all_triangulations(list(range(n)))
+    def bad_diagonals(tri_list):
+        bad = 0
+        for t in tri_list:
+            for a, b in ((t[0], t[1]), (t[1], t[2]), (t[2], t[0])):
+                if (b - a) % n in (1, n - 1):
+                    continue                    # polygon side (a face segment)
+                if coplanar(loop[a], loop[b]):
+                    bad += 1
+        return bad
+    best = min(cands, key=bad_diagonals)        # min() keeps the first minimum
+    assert bad_diagonals(best) == 0, loop
+    return [(loop[a], loop[b], loop[c]) for a, b, c in sorted(best)]
 
 
 def build():
@@ -116,12 +157,14 @@ def orientation_check(table, ntri):
     mid = np.array([(pos[a] + pos[b]) / 2 for a, b in EDGE_CORNERS])
     for case in range(1, 255):
         ins = np.array([(case >> i) & 1 for i in range(8)], bool)
-        # per loop (fans share their first edge id): area vector . sum(outside - inside endpoints) > 0
-        loops = {}
-        for t in range(ntri[case]):
-            e = [int(v) for v in table[case, 3 * t:3 * t + 3]]
-            loops.setdefault(e[0], []).append(e)
-        for fan in loops.values():
+        # per connected patch: area vector . sum(outside - inside endpoints) > 0
+        tl = [[int(v) for v in table[case, 3 * t:3 * t + 3]] for t in range(ntri[case])]
+        patches = []
+        for e in tl:
+            hit = [p for p in patches if any(set(e) & set(q) for q in p)]
+            merged = [e] + [q for p in hit for q in p]
+            patches = [p for p in patches if p not in hit] + [merged]
+        for fan in patches:
             area = np.zeros(3)
             grad = np.zeros(3)
             edges = set()
