@@ -289,7 +289,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=256)
-    ap.add_argument("--precision", default=os.environ.get("DISN_PRECISION", "fp32"), choices=["fp32", "bf16x3"])
+    ap.add_argument("--precision", default=os.environ.get("DISN_PRECISION", "bf16x3"), choices=["fp32", "bf16x3"])
     ap.add_argument("--cpu-sample", type=int, default=8192, dest="cpu_sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -329,6 +329,24 @@ int disn_write_dist(const char* path, int32_t res, const double* bbox, const flo
   return 0;
 }
 
+int disn_write_obj(const char* path, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces) {
+  DISN_REQUIRE(path && (verts || n_verts == 0) && (faces || n_faces == 0) && n_verts >= 0 && n_faces >= 0,
+               "bad write_obj arguments");
+  FILE* f = fopen(path, "w");
+  if (!f) { set_error(std::string("cannot open ") + path); return -3; }
+  std::vector<char> buf(1 << 20);
+  setvbuf(f, buf.data(), _IOFBF, buf.size());
+  fprintf(f, "# Generated by the DISN B200 marching-cubes post-pass\n# Number of vertices: %lld\n# Number of faces: %lld\n",
+          (long long)n_verts, (long long)n_faces);
+  for (int64_t i = 0; i < n_verts; ++i) fprintf(f, "v %g %g %g\n", verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]);
+  for (int64_t i = 0; i < n_faces; ++i)
+    fprintf(f, "f %d %d %d\n", faces[3 * i] + 1, faces[3 * i + 1] + 1, faces[3 * i + 2] + 1);
+  bool ok = !ferror(f);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { set_error(std::string("short write to ") + path); return -3; }
+  return 0;
+}
+
 int disn_marching_cubes(disn_ctx* c, const float* sdf, int32_t R, const double* bbox, float iso, float* verts,
                         int64_t* n_verts, int32_t* faces, int64_t* n_faces, uint32_t flags) {
   DISN_REQUIRE(c && sdf && bbox && n_verts && n_faces, "null argument");

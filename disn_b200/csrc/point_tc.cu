@@ -13,7 +13,7 @@
 //     epilogue warps (bias / folded image features, ReLU, bf16 hi/lo split) into a 3-slot ring of
 //     K-major 128B-swizzled A tiles that layer l+1's MMAs consume (K-outer), so MMA and epilogue pipeline;
 //   * weights are pre-split, pre-permuted and pre-swizzled on the host into the exact 16 KB shared-memory
-//     images the B operand needs and streamed by the bulk-copy engine (cp.async.bulk) through an 8-stage
+//     images the B operand needs and streamed by the bulk-copy engine (cp.async.bulk) through a 7-stage
 //     mbarrier ring; each CTA loads only its half of every B tile;
 //   * warp roles: 0 weight producer, 1 MMA issuer (leader CTA) / full-barrier relay (peer CTA),
 //     2 TMEM allocator, 4-7 epilogue (one TMEM lane each), 8-11 front end (points, projection, layer 1,

@@ -103,6 +103,10 @@ int disn_eval_grid(disn_ctx* ctx, const double* sdf_params, const float* trans_m
 /* .dist writer: int32 {-res,res,res}, double bbox[6], float32 values[(res+1)^3]. Host values. */
 int disn_write_dist(const char* path, int32_t res, const double* bbox, const float* values);
 
+/* OBJ writer in the conventions of the reference's mesher output (demo/result.obj): comment header with
+ * the counts, `v x y z` (%g), 1-based `f i j k`. Host arrays; faces are 0-based on input. */
+int disn_write_obj(const char* path, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces);
+
 /* Marching cubes of sdf[R,R,R] (z,y,x) at iso over bbox. Two-call protocol: pass verts=faces=NULL to
  * get counts, then call again with buffers of n_verts*3 floats / n_faces*3 int32 (0-based).
  * sdf is a host pointer unless DISN_DEVICE_PTR. Vertices are welded (shared per grid edge) and ordered
