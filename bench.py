@@ -156,9 +156,10 @@ def run_ours(args):
     R = args.res + 1
     total_pts = R ** 3
     # z-slab of this rank (contiguous in the output array: x fastest, z slowest)
-    z_bounds = [(r * R) // world for r in range(world + 1)]
-    z0, z1 = z_bounds[rank], z_bounds[rank + 1]
-    max_planes = max(z_bounds[i + 1] - z_bounds[i] for i in range(world))
+    from disn_b200 import sharding
+    z_bounds = sharding.z_bounds(R, world)
+    z0, z1 = sharding.slab(R, world, rank)
+    max_planes = sharding.max_planes(R, world)
 
     eng = Engine(device=local_rank, precision=args.precision, max_batch=1)
     W = synth.make_weights(seed=7, init="he")

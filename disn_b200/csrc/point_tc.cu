@@ -13,7 +13,7 @@
 //     epilogue warps (bias / folded image features, ReLU, bf16 hi/lo split) into a 3-slot ring of
 //     K-major 128B-swizzled A tiles that layer l+1's MMAs consume (K-outer), so MMA and epilogue pipeline;
 //   * weights are pre-split, pre-permuted and pre-swizzled on the host into the exact 16 KB shared-memory
-//     images the B operand needs and streamed by the bulk-copy engine (cp.async.bulk) through a 7-stage
+//     images the B operand needs and streamed by the bulk-copy engine (cp.async.bulk) through a 6-stage
 //     mbarrier ring; each CTA loads only its half of every B tile;
 //   * warp roles: 0 weight producer, 1 MMA issuer (leader CTA) / full-barrier relay (peer CTA),
 //     2 TMEM allocator, 4-7 epilogue (one TMEM lane each), 8-11 front end (points, projection, layer 1,
@@ -27,7 +27,7 @@
 namespace disn {
 namespace {
 
-constexpr int NW = 7;                 // weight ring stages
+constexpr int NW = 6;                 // weight ring stages
 constexpr int NX = 3;                 // activation (A operand) ring slots
 constexpr int NG = 2;                 // gather ring slots
 constexpr int W_STAGE = 16384;        // 128 rows x 64 k x bf16
@@ -36,6 +36,8 @@ constexpr int G_LD = 65;              // padded point stride of the gather ring
 constexpr int PTS = 64;               // points per CTA per tile
 constexpr int NTHREADS = 384;
 constexpr int STAGES_PER_STREAM = 66; // 2 + 16 + 32 + 16 weight stages (pair-level, 32 KB each)
+// shared-memory table of small fp32 parameters per stream
+constexpr int SB_B2 = 0, SB_B3 = 256, SB_B4 = 768, SB_B5 = 1280, SB_W6 = 1536, SB_W1 = 1792, SB_B1 = 1984, SB_STRIDE = 2048;
 constexpr int XSLOTS_PER_STREAM = 20; // 4 + 8 + 8 activation slices drained from TMEM (layer-1 output has its own slot)
 
 struct TcSmem {
@@ -43,12 +45,12 @@ struct TcSmem {
   alignas(1024) uint8_t x[NX][2][X_HALF];      // [slot][hi|lo]  ring written by the epilogue warps
   alignas(1024) uint8_t x2[2][X_HALF];         // fold1/conv1 output (layer-2 A operand) written by the front end
   float g[NG][64 * G_LD];                      // gathered image features [h*32+j][point]
+  float sb[2][SB_STRIDE];                      // per-stream small parameters (biases, fold2/conv5, fold1/conv1)
   float px[PTS], py[PTS], pz[PTS];
   int tap_off[PTS][4];
   float tap_w[PTS][4];
   float part[2][2][2][PTS];                    // [tile parity][stream][half][point]
   alignas(8) uint64_t wfull[NW];
-  uint64_t wpeer[NW];
   uint64_t wempty[NW];
   uint64_t xfull[NX];
   uint64_t xempty[NX];
@@ -100,7 +102,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
   const int my_tiles = (pair < total_tiles) ? (int)((total_tiles - pair + num_pairs - 1) / num_pairs) : 0;
 
   if (tid == 0) {
-    for (int i = 0; i < NW; ++i) { tc::mbar_init(&s.wfull[i], 1); tc::mbar_init(&s.wpeer[i], 1); tc::mbar_init(&s.wempty[i], 1); }
+    for (int i = 0; i < NW; ++i) { tc::mbar_init(&s.wfull[i], cta == 0 ? 2 : 1); tc::mbar_init(&s.wempty[i], 1); }
     for (int i = 0; i < NX; ++i) { tc::mbar_init(&s.xfull[i], 8); tc::mbar_init(&s.xempty[i], 1); }
     tc::mbar_init(&s.x2full, 8);
     tc::mbar_init(&s.x2empty, 1);
@@ -109,6 +111,20 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     tc::mbar_init(&s.acc5_free, 8);
     tc::fence_barrier_init();
   }
+  for (int i = tid; i < 2 * SB_STRIDE; i += NTHREADS) {   // small parameters -> shared memory, once
+    const StreamWeights& w = (i >= SB_STRIDE) ? job.l : job.g;
+    const int o = i % SB_STRIDE;
+    float v;
+    if (o < SB_B3) v = w.b2[o - SB_B2];
+    else if (o < SB_B4) v = w.b3[o - SB_B3];
+    else if (o < SB_B5) v = w.b4[o - SB_B4];
+    else if (o < SB_W6) v = w.b5[o - SB_B5];
+    else if (o < SB_W1) v = w.w6[o - SB_W6];
+    else if (o < SB_B1) v = w.w1[o - SB_W1];
+    else v = w.b1[o - SB_B1];
+    s.sb[i / SB_STRIDE][o] = v;
+  }
+  __syncthreads();
   if (warp == 2) {
     tc::tmem_alloc_cg2(&s.tmem_base, 512);
     tc::tmem_relinquish_cg2();
@@ -133,28 +149,25 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     }
   } else if (warp == 1) {
     if (cta == 1) {
-      // ===================== relay: peer's weight stages are resident =====================
+      // ===================== relay: this CTA's half of a weight stage has landed -> tell the leader ==========
       if (lane == 0) {
         uint32_t seq = 0;
         for (int it = 0; it < my_tiles; ++it)
           for (int g = 0; g < 2 * STAGES_PER_STREAM; ++g, ++seq) {
             const int st = seq % NW;
             tc::mbar_wait(&s.wfull[st], (seq / NW) & 1);
-            tc::mbar_arrive_cluster(&s.wpeer[st], 0);
+            tc::mbar_arrive_cluster(&s.wfull[st], 0);      // leader's wfull counts {own expect_tx, this arrive}
           }
       }
-    } else if (lane == 0) {
-      // ===================== MMA issuer (leader CTA, one thread) =====================
+    } else {
+      // ===================== MMA issuer (leader CTA) =====================
+      // The whole warp runs the loop so every address/descriptor is warp-uniform (uniform registers);
+      // a single elected lane issues the tcgen05 instructions.
       const uint32_t idesc = tc::make_idesc_bf16(128, 256);
+      const uint32_t w_lo0 = tc::desc_lo(tc::smem_u32(s.w[0]));          // + st * (W_STAGE >> 4)
+      const uint32_t x_lo0 = tc::desc_lo(tc::smem_u32(s.x[0][0]));       // + slot * (2*X_HALF >> 4), lo = + X_HALF >> 4
+      const uint32_t x2_lo0 = tc::desc_lo(tc::smem_u32(s.x2[0]));
       uint32_t wseq = 0, xseq = 0, nstream = 0;
-      auto wait_w = [&](uint32_t sq) -> uint64_t {
-        const int st = sq % NW;
-        const uint32_t ph = (sq / NW) & 1;
-        tc::mbar_wait(&s.wfull[st], ph);
-        tc::mbar_wait_cluster(&s.wpeer[st], ph);
-        tc::tc_fence_after_sync();
-        return tc::make_desc_sw128(tc::smem_u32(s.w[st]));
-      };
       for (int it = 0; it < my_tiles; ++it) {
         for (int sidx = 0; sidx < 2; ++sidx, ++nstream) {
 #pragma unroll 1
@@ -163,52 +176,61 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
             const int nnb = (layer == 1 || layer == 2) ? 2 : 1;
             const uint32_t colbase = (layer & 1) ? 256u : 0u;
             if (layer == 1 && nstream > 0) {   // acc3 overwrites the columns the previous stream's acc5 used
-              tc::mbar_wait_cluster(&s.acc5_free, (nstream - 1) & 1);
+              tc::mbar_wait(&s.acc5_free, (nstream - 1) & 1);
               tc::tc_fence_after_sync();
             }
 #pragma unroll 1
             for (int t = 0; t < nsl; ++t) {
               const int slot = xseq % NX;
-              uint64_t a_hi, a_lo;
+              uint32_t a_hi;
               if (layer == 0) {      // A operand = layer-1 output staged by the front end
-                tc::mbar_wait_cluster(&s.x2full, nstream & 1);
-                tc::tc_fence_after_sync();
-                a_hi = tc::make_desc_sw128(tc::smem_u32(s.x2[0]));
-                a_lo = tc::make_desc_sw128(tc::smem_u32(s.x2[1]));
+                tc::mbar_wait(&s.x2full, nstream & 1);
+                a_hi = x2_lo0;
               } else {
-                tc::mbar_wait_cluster(&s.xfull[slot], (xseq / NX) & 1);
-                tc::tc_fence_after_sync();
-                a_hi = tc::make_desc_sw128(tc::smem_u32(s.x[slot][0]));
-                a_lo = tc::make_desc_sw128(tc::smem_u32(s.x[slot][1]));
+                tc::mbar_wait(&s.xfull[slot], (xseq / NX) & 1);
+                a_hi = x_lo0 + (uint32_t)slot * ((2 * X_HALF) >> 4);
               }
+              const uint32_t a_lo = a_hi + (X_HALF >> 4);
+              tc::tc_fence_after_sync();
 #pragma unroll 1
               for (int nb = 0; nb < nnb; ++nb) {
                 const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
-                uint64_t bdesc = wait_w(wseq);
+                // ---- stage "hi": A_hi*W_hi and A_lo*W_hi ----
+                int st = wseq % NW;
+                tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1);
+                tc::tc_fence_after_sync();
+                uint32_t b = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
+                if (tc::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc::mma_cg2(d, tc::desc_advance_k(a_hi, k * 16), tc::desc_advance_k(bdesc, k * 16), idesc,
-                              (t | k) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b + 2u * k, idesc, (t | k) ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc::mma_cg2(d, tc::desc_advance_k(a_lo, k * 16), tc::desc_advance_k(bdesc, k * 16), idesc, 1u);
-                tc::commit_cg2(&s.wempty[wseq % NW], 0b11);
+                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_lo + 2u * k, b + 2u * k, idesc, 1u);
+                  tc::commit_cg2(&s.wempty[st], 0b11);
+                }
+                __syncwarp();
                 ++wseq;
-                bdesc = wait_w(wseq);
+                // ---- stage "lo": A_hi*W_lo ----
+                st = wseq % NW;
+                tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1);
+                tc::tc_fence_after_sync();
+                b = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
+                if (tc::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc::mma_cg2(d, tc::desc_advance_k(a_hi, k * 16), tc::desc_advance_k(bdesc, k * 16), idesc, 1u);
-                tc::commit_cg2(&s.wempty[wseq % NW], 0b11);
+                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b + 2u * k, idesc, 1u);
+                  tc::commit_cg2(&s.wempty[st], 0b11);
+                }
+                __syncwarp();
                 ++wseq;
               }
-              if (layer == 0) {
-                tc::commit_cg2(&s.x2empty, 0b11);
-              } else {
-                tc::commit_cg2(&s.xempty[slot], 0b11);
-                ++xseq;
+              if (tc::elect_one()) {
+                if (layer == 0) tc::commit_cg2(&s.x2empty, 0b11);
+                else tc::commit_cg2(&s.xempty[slot], 0b11);
               }
+              __syncwarp();
+              if (layer != 0) ++xseq;
             }
-            tc::commit_cg2(&s.acc_full[layer], 0b11);
+            if (tc::elect_one()) tc::commit_cg2(&s.acc_full[layer], 0b11);
+            __syncwarp();
           }
         }
       }
@@ -230,7 +252,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       }
     };
     // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into activation slice `seq`
-    auto drain = [&](uint32_t col0, int t, const float* __restrict__ bias, uint32_t seq, bool gather) {
+    auto drain = [&](uint32_t col0, int t, const float* bias, uint32_t seq, bool gather) {
       const int slot = seq % NX;
       tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
       uint32_t r[32];
@@ -239,7 +261,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 bq = __ldg(reinterpret_cast<const float4*>(bias + f0 + j));
+        const float4 bq = *reinterpret_cast<const float4*>(bias + f0 + j);
         v[j] = bq.x; v[j + 1] = bq.y; v[j + 2] = bq.z; v[j + 3] = bq.w;
       }
       if (gather) {
@@ -262,21 +284,21 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     for (int it = 0; it < my_tiles; ++it) {
       const TileCoord tc0 = tile_coord((int64_t)pair + (int64_t)it * num_pairs, tiles_per_img);
       for (int sidx = 0; sidx < 2; ++sidx) {
-        const StreamWeights& w = sidx ? job.l : job.g;
+        const float* sb = s.sb[sidx];
         const uint32_t seq0 = (uint32_t)it * (2 * XSLOTS_PER_STREAM) + sidx * XSLOTS_PER_STREAM;
         const uint32_t par = (uint32_t)(it * 2 + sidx) & 1;
         // fold1/conv2 output (256) -> X3
         tc::mbar_wait(&s.acc_full[0], par);
         tc::tc_fence_after_sync();
-        for (int t = 0; t < 4; ++t) drain(0u, t, w.b2, seq0 + t, false);
+        for (int t = 0; t < 4; ++t) drain(0u, t, sb + SB_B2, seq0 + t, false);
         // fold1/conv3 output (512) -> X4
         tc::mbar_wait(&s.acc_full[1], par);
         tc::tc_fence_after_sync();
-        for (int t = 0; t < 8; ++t) drain(256u, t, w.b3, seq0 + 4 + t, false);
+        for (int t = 0; t < 8; ++t) drain(256u, t, sb + SB_B3, seq0 + 4 + t, false);
         // fold2/conv1 output (512) + folded image features -> X5
         tc::mbar_wait(&s.acc_full[2], par);
         tc::tc_fence_after_sync();
-        const float* b4 = sidx ? w.b4 : (job.gbias + (int64_t)tc0.b * kHidden);
+        const float* b4 = sidx ? (sb + SB_B4) : (job.gbias + (int64_t)tc0.b * kHidden);
         for (int t = 0; t < 8; ++t) drain(0u, t, b4, seq0 + 12 + t, sidx == 1);
         // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
         tc::mbar_wait(&s.acc_full[3], par);
@@ -289,8 +311,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
           tc::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float a = fmaxf(__uint_as_float(r[j]) + __ldg(w.b5 + f0 + j), 0.f);
-            part = fmaf(a, __ldg(w.w6 + f0 + j), part);
+            float a = fmaxf(__uint_as_float(r[j]) + sb[SB_B5 + f0 + j], 0.f);
+            part = fmaf(a, sb[SB_W6 + f0 + j], part);
           }
         }
         tc::tc_fence_before_sync();
@@ -321,17 +343,17 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     const int fw = warp - 8;
     const int Wm = job.img_w, Hm = job.img_h;
 
-    auto stage_x2 = [&](const StreamWeights& w, uint32_t use) {   // use = running stream count
+    auto stage_x2 = [&](const float* sb, uint32_t use) {   // use = running stream count
       tc::mbar_wait(&s.x2empty, (use & 1) ^ 1);
       const float x = s.px[p], y = s.py[p], z = s.pz[p];
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int f = h * 32 + j;
-        float a = __ldg(w.b1 + f);
-        a = fmaf(x, __ldg(w.w1 + f), a);
-        a = fmaf(y, __ldg(w.w1 + 64 + f), a);
-        a = fmaf(z, __ldg(w.w1 + 128 + f), a);
+        float a = sb[SB_B1 + f];
+        a = fmaf(x, sb[SB_W1 + f], a);
+        a = fmaf(y, sb[SB_W1 + 64 + f], a);
+        a = fmaf(z, sb[SB_W1 + 128 + f], a);
         v[j] = fmaxf(a, 0.f);
       }
       store_slice(s.x2[0], s.x2[1], p, h, v);
@@ -400,8 +422,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         for (int k = 0; k < 4; ++k) { s.tap_off[ft][k] = off[k]; s.tap_w[ft][k] = wg[k]; }
       }
       named_bar_sync(2, 128);
-      stage_x2(job.g, (uint32_t)it * 2);
-      stage_x2(job.l, (uint32_t)it * 2 + 1);
+      stage_x2(s.sb[0], (uint32_t)it * 2);
+      stage_x2(s.sb[1], (uint32_t)it * 2 + 1);
       // gather of the projected feature map for the local stream's fold2/conv1 epilogue
       const float* pm = job.pmap + (int64_t)b * Hm * Wm * kHidden;
       const int grp = lane >> 3, q = lane & 7;

@@ -167,6 +167,33 @@ __device__ __forceinline__ void commit_cg2(uint64_t* bar, uint16_t cta_mask) {
                : "memory");
 }
 
+// --- warp-uniform issue path: the whole MMA warp runs the loop, one elected lane issues ----------------
+// (keeps descriptors/addresses in uniform registers instead of ELECT+R2UR per operand in divergent code)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// high 32 bits of every K-major SW128 descriptor (SBO=64, version=1, layout_type=2); low word = addr>>4 | LBO
+constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void mma_cg2_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi), "r"(0u)
+      : "memory");
+}
+
 // swizzled byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a K-major SW128 tile
 __host__ __device__ constexpr uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);

@@ -1,0 +1,118 @@
+"""CPU tests of the reference-compatible Python surface, host-only C-ABI entry points and the multi-rank
+slab logic (gloo, world_size 2)."""
+import os
+import tempfile
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+
+def _flags(**kw):
+    from disn_b200 import create_sdf as cs
+    return cs.default_flags(**kw)
+
+
+def test_placeholders_and_end_points_keys_match_reference():
+    from disn_b200 import model_normalization as model
+    F = _flags()
+    pls = model.placeholder_inputs(2, 1, (137, 137), num_sample_pc=100, scope="inputs_pl", FLAGS=F)
+    # models/model_normalization.py:27-35
+    assert set(pls) == {"pc", "sample_pc", "sample_pc_rot", "imgs", "sdf", "sdf_params", "trans_mat"}
+    assert pls["imgs"].shape == (2, 137, 137, 3) and pls["trans_mat"].shape == (2, 4, 3)
+    assert pls["sample_pc"].shape == (2, 100, 3) and pls["sdf"].shape == (2, 100, 1)
+    ep = model.get_model(pls, 1, model.Placeholder("is_training", ()), bn=False, FLAGS=F)
+    # models/model_normalization.py:60-63,73,79,205-219
+    for k in ("ref_pc", "ref_sdf", "ref_img", "resized_ref_img", "img_embedding", "pred_sdf_value_global",
+              "pred_sdf_value_local", "pred_sdf", "sample_img_points", "ref_feats_embedding_cnn", "point_img_feat"):
+        assert k in ep, k
+    loss, ep = model.get_loss(ep, sdf_weight=10., num_sample_points=100, FLAGS=F)
+    assert set(ep["losses"]) >= {"accuracy", "sdf_loss", "sdf_loss_realvalue", "overall_loss"}
+    feats = model.placeholder_features(2, 100)
+    assert feats["point_img_feat"].shape == (2, 100, 1, 1472)
+
+
+@pytest.mark.parametrize("flag", ["binary", "threedcnn", "img_feat_onestream", "multi_view", "alpha"])
+def test_out_of_scope_branches_are_refused_loudly(flag):
+    from disn_b200 import model_normalization as model
+    F = _flags(**{flag: True})
+    pls = model.placeholder_inputs(1, 1, (137, 137), num_sample_pc=8, FLAGS=_flags())
+    with pytest.raises(NotImplementedError, match=flag):
+        model.get_model(pls, 1, None, FLAGS=F)
+
+
+def test_driver_constants_match_reference_arithmetic(golden, tmp_path):
+    from disn_b200 import create_sdf as cs
+    for sdf_res, R, total, split, nsp in golden["chunking"]["table"]:
+        cs.configure(_flags(sdf_res=int(sdf_res), log_dir=str(tmp_path / ("log%d" % sdf_res))))
+        assert (cs.RESOLUTION, cs.TOTAL_POINTS, cs.SPLIT_SIZE, cs.NUM_SAMPLE_POINTS) == (R, total, split, nsp)
+        assert cs.RESULT_OBJ_PATH.endswith(os.path.join("test_objs", "%d_0.0" % R))
+    from oracle import disn_oracle as orc
+    cs.configure(_flags(sdf_res=6, log_dir=str(tmp_path / "g")))
+    np.testing.assert_array_equal(cs.build_grid_points([-1, -1, -1, 1, 1, 1])[0],
+                                  orc.grid_points([-1, -1, -1, 1, 1, 1], 7))
+
+
+def test_dist_roundtrip_and_obj_writer(golden, tmp_path):
+    from disn_b200 import create_sdf as cs
+    g = golden["dist_roundtrip"]
+    res = int(g["res"])
+    fn = str(tmp_path / "t.dist")
+    cs.to_binary(res, list(g["bbox"]), g["values"].astype(np.float64), fn)
+    assert np.array_equal(np.fromfile(fn, dtype=np.uint8), g["file_bytes"])     # == reference reader's input
+    r2, bbox, vals = cs.read_dist(fn)
+    assert r2 == res and np.array_equal(vals.reshape(-1), g["values"]) and np.allclose(bbox, g["bbox"])
+    # OBJ conventions of demo/result.obj: '# Number of vertices', 'v %g %g %g', 1-based faces
+    v = np.array([[0.46875, -0.179688, -0.382966], [1, 2, 3], [0.5, 0.25, 1e-7]], np.float32)
+    f = np.array([[0, 1, 2]], np.int32)
+    on = str(tmp_path / "m.obj")
+    cs.write_obj(on, v, f)
+    lines = open(on).read().splitlines()
+    assert lines[1] == "# Number of vertices: 3" and lines[2] == "# Number of faces: 1"
+    assert lines[3] == "v 0.46875 -0.179688 -0.382966" and lines[-1] == "f 1 2 3"
+    with pytest.raises(ValueError):
+        open(fn, "ab").write(b"xx")
+        cs.read_dist(fn)
+
+
+def test_slab_partition_properties():
+    from disn_b200 import sharding
+    for R in (9, 65, 129, 257, 513):
+        for world in (1, 2, 3, 4, 8):
+            b = sharding.z_bounds(R, world)
+            assert b[0] == 0 and b[-1] == R and all(b[i] <= b[i + 1] for i in range(world))
+            sizes = [b[i + 1] - b[i] for i in range(world)]
+            assert max(sizes) - min(sizes) <= 1 and max(sizes) == sharding.max_planes(R, world)
+    assert sharding.z_bounds(257, 8) == [0, 32, 64, 96, 128, 160, 192, 224, 257]
+
+
+def _gloo_worker(rank, world, R, port, outdir):
+    import torch
+    import torch.distributed as dist
+    from disn_b200 import sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    z0, z1 = sharding.slab(R, world, rank)
+    mp = sharding.max_planes(R, world)
+    zz, yy, xx = torch.meshgrid(torch.arange(z0, z1), torch.arange(R), torch.arange(R), indexing="ij")
+    slab = torch.zeros((mp, R, R))
+    slab[:z1 - z0] = (zz * R * R + yy * R + xx).float()          # stand-in for the rank's SDF slab
+    full = torch.empty((world * mp, R, R))
+    dist.all_gather_into_tensor(full, slab)
+    out = sharding.unpack_gathered(full, R, world, torch.empty((R, R, R)))
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                      # the bench's max-over-ranks timing reduction
+    if rank == 0:
+        np.save(os.path.join(outdir, "full.npy"), out.numpy())
+        np.save(os.path.join(outdir, "tmax.npy"), t.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("R", [9, 17])
+def test_two_rank_slab_gather_gloo(R, tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + R
+    mp.spawn(_gloo_worker, args=(2, R, port, str(tmp_path)), nprocs=2, join=True)
+    full = np.load(tmp_path / "full.npy")
+    np.testing.assert_array_equal(full.reshape(-1), np.arange(R ** 3, dtype=np.float32))
+    assert np.load(tmp_path / "tmax.npy")[0] == 2.0
