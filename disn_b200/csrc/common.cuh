@@ -98,7 +98,9 @@ struct disn_ctx {
   float* proj[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // per-level projected maps [B,h,h,512]
   float* fc_a = nullptr;        // [B,4096]
   float* fc_b = nullptr;        // [B,4096]
-  float* partial = nullptr;     // split-K partials
+  float* partial = nullptr;     // split-K partials (fc layers)
+  float* splitk_ws = nullptr;   // split-K partials (conv / projection GEMMs)
+  int64_t splitk_ws_elems = 0;
   float* emb = nullptr;         // [B,num_classes]
   float* gbias = nullptr;       // [B,512]
   float* pmap = nullptr;        // [B,img_h,img_w,512]

@@ -51,7 +51,8 @@ struct ConvGeom { int H, W, Cin; };
 template <int BN, int MODE, bool VEC>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                        const float* __restrict__ bias, float* __restrict__ C,
-                                                       int M, int N, int K, int relu, ConvGeom g) {
+                                                       int M, int N, int K, int relu, ConvGeom g, int kper,
+                                                       float* __restrict__ ws) {
   constexpr int BM = 128, BK = 8;
   constexpr int TN = 8;
   constexpr int TX = BN / TN;        // threads along N: 16 (BN=128) or 8 (BN=64)
@@ -134,11 +135,14 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     if (tid < BVEC) *reinterpret_cast<float4*>(&Bs[b_row][b_col]) = b_reg;
   };
 
-  load_tiles(0);
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  // split-K: blockIdx.z owns k in [k_begin, k_end); partial sums go to the workspace, reduced afterwards
+  const int k_begin = blockIdx.z * kper;
+  const int k_end = min(K, k_begin + kper);
+  load_tiles(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
     store_tiles();
     __syncthreads();
-    if (k0 + BK < K) load_tiles(k0 + BK);
+    if (k0 + BK < k_end) load_tiles(k0 + BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[TM], b[TN];
@@ -164,6 +168,12 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       int n = n0 + h * (BN / 2) + tx * 4;
       float4 o;
       float* op = reinterpret_cast<float*>(&o);
+      if (ws) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) op[j] = acc[i][h * 4 + j];
+        *reinterpret_cast<float4*>(ws + ((int64_t)blockIdx.z * M + m) * N + n) = o;
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v = acc[i][h * 4 + j] + (bias ? bias[n + j] : 0.f);
@@ -174,33 +184,66 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
   }
 }
 
+// C[m,n] = act(bias[n] + sum_z ws[z,m,n])
+__global__ void splitk_reduce_kernel(const float4* __restrict__ ws, const float* __restrict__ bias,
+                                     float4* __restrict__ C, int64_t MN4, int N4, int splits, int relu) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < MN4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = ws[i];
+    for (int z = 1; z < splits; ++z) {
+      const float4 v = ws[(int64_t)z * MN4 + i];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    if (bias) {
+      const float4 b = reinterpret_cast<const float4*>(bias)[i % N4];
+      s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+    }
+    if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+    C[i] = s;
+  }
+}
+
+template <int BN>
+static void gemm_dispatch(int mode, bool vec, dim3 grid, cudaStream_t st, const float* A, const float* Bm,
+                          const float* bias, float* C, int M, int N, int K, int relu, ConvGeom g, int kper, float* ws) {
+  dim3 block(256);
+  if (mode == A_PLAIN) {
+    if (vec) gemm_f32_kernel<BN, A_PLAIN, true><<<grid, block, 0, st>>>(A, Bm, bias, C, M, N, K, relu, g, kper, ws);
+    else gemm_f32_kernel<BN, A_PLAIN, false><<<grid, block, 0, st>>>(A, Bm, bias, C, M, N, K, relu, g, kper, ws);
+  } else {
+    if (vec) gemm_f32_kernel<BN, A_IM2COL, true><<<grid, block, 0, st>>>(A, Bm, bias, C, M, N, K, relu, g, kper, ws);
+    else gemm_f32_kernel<BN, A_IM2COL, false><<<grid, block, 0, st>>>(A, Bm, bias, C, M, N, K, relu, g, kper, ws);
+  }
+}
+
 static int launch_gemm(disn_ctx* c, int mode, const float* A, const float* Bm, const float* bias, float* C, int M,
                        int N, int K, int relu, ConvGeom g) {
   bool vec = (mode == A_PLAIN) ? (K % 4 == 0) : (g.Cin % 4 == 0);
-  dim3 block(256);
-  if (N % 128 == 0) {
-    dim3 grid(N / 128, (M + 127) / 128);
-    if (mode == A_PLAIN) {
-      if (vec) gemm_f32_kernel<128, A_PLAIN, true><<<grid, block, 0, c->stream>>>(A, Bm, bias, C, M, N, K, relu, g);
-      else gemm_f32_kernel<128, A_PLAIN, false><<<grid, block, 0, c->stream>>>(A, Bm, bias, C, M, N, K, relu, g);
-    } else {
-      if (vec) gemm_f32_kernel<128, A_IM2COL, true><<<grid, block, 0, c->stream>>>(A, Bm, bias, C, M, N, K, relu, g);
-      else gemm_f32_kernel<128, A_IM2COL, false><<<grid, block, 0, c->stream>>>(A, Bm, bias, C, M, N, K, relu, g);
-    }
-  } else if (N % 64 == 0) {
-    dim3 grid(N / 64, (M + 127) / 128);
-    if (mode == A_PLAIN) {
-      if (vec) gemm_f32_kernel<64, A_PLAIN, true><<<grid, block, 0, c->stream>>>(A, Bm, bias, C, M, N, K, relu, g);
-      else gemm_f32_kernel<64, A_PLAIN, false><<<grid, block, 0, c->stream>>>(A, Bm, bias, C, M, N, K, relu, g);
-    } else {
-      if (vec) gemm_f32_kernel<64, A_IM2COL, true><<<grid, block, 0, c->stream>>>(A, Bm, bias, C, M, N, K, relu, g);
-      else gemm_f32_kernel<64, A_IM2COL, false><<<grid, block, 0, c->stream>>>(A, Bm, bias, C, M, N, K, relu, g);
-    }
-  } else {
-    set_error("gemm: N must be a multiple of 64");
-    return -2;
+  const int BN = (N % 128 == 0) ? 128 : 64;
+  if (N % 64 != 0) { set_error("gemm: N must be a multiple of 64"); return -2; }
+  const int ctas = (N / BN) * ((M + 127) / 128);
+  // split-K so that small late layers (few output tiles) still fill 148 SMs for ~2 waves
+  int splits = 1;
+  if (K % 8 == 0 && ctas < 148) {
+    const int kchunks = K / 64 > 0 ? K / 64 : 1;             // keep >= 64 k per split
+    int want = (296 + ctas - 1) / ctas;
+    if (want > kchunks) want = kchunks;
+    for (int d = want; d >= 1; --d)
+      if ((K / 8) % d == 0) { splits = d; break; }
+    if ((int64_t)splits * M * N > c->splitk_ws_elems) splits = 1;
   }
+  const int kper = (splits == 1) ? K : K / splits;
+  dim3 grid(N / BN, (M + 127) / 128, splits);
+  float* ws = splits > 1 ? c->splitk_ws : nullptr;
+  if (BN == 128) gemm_dispatch<128>(mode, vec, grid, c->stream, A, Bm, bias, C, M, N, K, relu, g, kper, ws);
+  else gemm_dispatch<64>(mode, vec, grid, c->stream, A, Bm, bias, C, M, N, K, relu, g, kper, ws);
   c->launches++;
+  if (splits > 1) {
+    const int64_t mn4 = (int64_t)M * N / 4;
+    int blocks = (int)std::min<int64_t>((mn4 + 255) / 256, 148 * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(ws), bias,
+                                                       reinterpret_cast<float4*>(C), mn4, N / 4, splits, relu);
+    c->launches++;
+  }
   DISN_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -348,7 +391,8 @@ void encoder_free(disn_ctx* c) {
   auto fr = [](float*& p) { if (p) cudaFree(p); p = nullptr; };
   fr(c->img_in); fr(c->img_rs); fr(c->act[0]); fr(c->act[1]);
   for (int i = 0; i < 5; ++i) { fr(c->taps[i]); fr(c->proj[i]); }
-  fr(c->fc_a); fr(c->fc_b); fr(c->partial); fr(c->emb); fr(c->gbias); fr(c->pmap);
+  fr(c->fc_a); fr(c->fc_b); fr(c->partial); fr(c->emb); fr(c->gbias); fr(c->pmap); fr(c->splitk_ws);
+  c->splitk_ws_elems = 0;
   c->alloc_B = 0;
 }
 
@@ -372,6 +416,8 @@ int encoder_alloc(disn_ctx* c, int B) {
   if (al(c->emb, Bn * c->cfg.num_classes)) return -1;
   if (al(c->gbias, Bn * kHidden)) return -1;
   if (al(c->pmap, Bn * c->cfg.img_h * c->cfg.img_w * kHidden)) return -1;
+  c->splitk_ws_elems = Bn * 8 * 1024 * 1024;       // 32 MB per image of split-K partial sums
+  if (al(c->splitk_ws, c->splitk_ws_elems)) return -1;
   c->alloc_B = B;
   return 0;
 }

@@ -18,6 +18,8 @@
 //   * warp roles: 0 weight producer, 1 MMA issuer (leader CTA) / full-barrier relay (peer CTA),
 //     2 TMEM allocator, 4-7 epilogue (one TMEM lane each), 8-11 front end (points, projection, layer 1,
 //     bilinear gather of the projected feature map into a shared-memory ring).
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -92,7 +94,8 @@ __device__ __forceinline__ void store_slice(uint8_t* xhi, uint8_t* xlo, int p, i
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per_img) {
+point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per_img,
+                unsigned long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const uint32_t cta = tc::cluster_ctarank();
@@ -133,6 +136,19 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
   tc::cluster_sync();
   tc::tc_fence_after_sync();
   const uint32_t tmem = s.tmem_base;
+  // optional wait-time accounting (DISN_TC_TRACE=1): cycles each role spends blocked on each barrier class
+  unsigned long long wt[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_role0 = dbg ? clock64() : 0;
+#define TIMED_WAIT(slot, call)                          \
+  do {                                                  \
+    if (dbg) {                                          \
+      const long long _t = clock64();                   \
+      call;                                             \
+      wt[slot] += (unsigned long long)(clock64() - _t); \
+    } else {                                            \
+      call;                                             \
+    }                                                   \
+  } while (0)
 
   if (warp == 0) {
     // ===================== weight producer (bulk-copy engine) =====================
@@ -176,7 +192,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
             const int nnb = (layer == 1 || layer == 2) ? 2 : 1;
             const uint32_t colbase = (layer & 1) ? 256u : 0u;
             if (layer == 1 && nstream > 0) {   // acc3 overwrites the columns the previous stream's acc5 used
-              tc::mbar_wait(&s.acc5_free, (nstream - 1) & 1);
+              TIMED_WAIT(2, tc::mbar_wait(&s.acc5_free, (nstream - 1) & 1));
               tc::tc_fence_after_sync();
             }
 #pragma unroll 1
@@ -184,10 +200,10 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
               const int slot = xseq % NX;
               uint32_t a_hi;
               if (layer == 0) {      // A operand = layer-1 output staged by the front end
-                tc::mbar_wait(&s.x2full, nstream & 1);
+                TIMED_WAIT(1, tc::mbar_wait(&s.x2full, nstream & 1));
                 a_hi = x2_lo0;
               } else {
-                tc::mbar_wait(&s.xfull[slot], (xseq / NX) & 1);
+                TIMED_WAIT(1, tc::mbar_wait(&s.xfull[slot], (xseq / NX) & 1));
                 a_hi = x_lo0 + (uint32_t)slot * ((2 * X_HALF) >> 4);
               }
               const uint32_t a_lo = a_hi + (X_HALF >> 4);
@@ -197,7 +213,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                 const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
                 // ---- stage "hi": A_hi*W_hi and A_lo*W_hi ----
                 int st = wseq % NW;
-                tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1);
+                TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1));
                 tc::tc_fence_after_sync();
                 uint32_t b = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
                 if (tc::elect_one()) {
@@ -211,7 +227,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                 ++wseq;
                 // ---- stage "lo": A_hi*W_lo ----
                 st = wseq % NW;
-                tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1);
+                TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1));
                 tc::tc_fence_after_sync();
                 b = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
                 if (tc::elect_one()) {
@@ -234,6 +250,10 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
           }
         }
       }
+      if (dbg && lane == 0) {
+        unsigned long long* o = dbg + (size_t)blockIdx.x * 16;
+        o[0] = (unsigned long long)(clock64() - t_role0); o[1] = wt[0]; o[2] = wt[1]; o[3] = wt[2];
+      }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue: TMEM -> bias/ReLU/split -> A-tile ring =====================
@@ -254,7 +274,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into activation slice `seq`
     auto drain = [&](uint32_t col0, int t, const float* bias, uint32_t seq, bool gather) {
       const int slot = seq % NX;
-      tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
+      TIMED_WAIT(3, tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1));
       uint32_t r[32];
       tc::tmem_ld_x32(tlane + col0 + 32u * t, r);
       const int f0 = fout(h, 32 * t);
@@ -266,7 +286,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       }
       if (gather) {
         const int gs = gseq % NG;
-        tc::mbar_wait(&s.gfull[gs], (gseq / NG) & 1);
+        TIMED_WAIT(5, tc::mbar_wait(&s.gfull[gs], (gseq / NG) & 1));
         const float* gp = s.g[gs] + (h * 32) * G_LD + p;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += gp[j * G_LD];
@@ -288,20 +308,20 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         const uint32_t seq0 = (uint32_t)it * (2 * XSLOTS_PER_STREAM) + sidx * XSLOTS_PER_STREAM;
         const uint32_t par = (uint32_t)(it * 2 + sidx) & 1;
         // fold1/conv2 output (256) -> X3
-        tc::mbar_wait(&s.acc_full[0], par);
+        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[0], par));
         tc::tc_fence_after_sync();
         for (int t = 0; t < 4; ++t) drain(0u, t, sb + SB_B2, seq0 + t, false);
         // fold1/conv3 output (512) -> X4
-        tc::mbar_wait(&s.acc_full[1], par);
+        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[1], par));
         tc::tc_fence_after_sync();
         for (int t = 0; t < 8; ++t) drain(256u, t, sb + SB_B3, seq0 + 4 + t, false);
         // fold2/conv1 output (512) + folded image features -> X5
-        tc::mbar_wait(&s.acc_full[2], par);
+        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[2], par));
         tc::tc_fence_after_sync();
         const float* b4 = sidx ? (sb + SB_B4) : (job.gbias + (int64_t)tc0.b * kHidden);
         for (int t = 0; t < 8; ++t) drain(0u, t, b4, seq0 + 12 + t, sidx == 1);
         // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
-        tc::mbar_wait(&s.acc_full[3], par);
+        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[3], par));
         tc::tc_fence_after_sync();
         float part = 0.f;
         for (int t = 0; t < 4; ++t) {
@@ -335,6 +355,10 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
           job.out_pred[(int64_t)tc0.b * job.N + n] = r * job.out_scale;
         }
       }
+    }
+    if (dbg && tid == 128) {
+      unsigned long long* o = dbg + (size_t)blockIdx.x * 16;
+      o[4] = (unsigned long long)(clock64() - t_role0); o[5] = wt[3]; o[6] = wt[4]; o[7] = wt[5];
     }
   } else if (warp >= 8) {
     // ===================== front end: points, projection, layer 1, feature gather =====================
@@ -534,10 +558,31 @@ int launch_point_tc(disn_ctx* c, const PointJob& job) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
   int pairs = (int)std::min<int64_t>(total, sms / 2);
+  unsigned long long* dbg = nullptr;
+  const bool trace = getenv("DISN_TC_TRACE") != nullptr;
+  if (trace) {
+    DISN_CUDA_OK(cudaMalloc(&dbg, (size_t)pairs * 2 * 16 * sizeof(unsigned long long)));
+    DISN_CUDA_OK(cudaMemsetAsync(dbg, 0, (size_t)pairs * 2 * 16 * sizeof(unsigned long long), c->stream));
+  }
   point_tc_kernel<<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(c->tc_weights),
-                                                           tiles_per_img);
+                                                           tiles_per_img, dbg);
   c->launches++;
   DISN_CUDA_OK(cudaGetLastError());
+  if (trace) {   // debug only: per-role blocked cycles, averaged over CTAs
+    std::vector<unsigned long long> h((size_t)pairs * 2 * 16);
+    DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+    DISN_CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < pairs; ++p) {
+      for (int k = 0; k < 4; ++k) a[k] += (double)h[(size_t)(2 * p) * 16 + k] / pairs;                 // leader's MMA warp
+      for (int k = 4; k < 8; ++k) a[k] += 0.5 * ((double)h[(size_t)(2 * p) * 16 + k] + (double)h[(size_t)(2 * p + 1) * 16 + k]) / pairs;
+    }
+    const double tiles = (double)total / pairs;
+    fprintf(stderr, "[DISN_TC_TRACE] tiles/pair=%.1f  per-tile cycles: MMA warp total=%.0f wait{weights=%.0f, act=%.0f, acc5=%.0f} | "
+                    "epilogue warp total=%.0f wait{xempty=%.0f, acc_full=%.0f, gather=%.0f}\n",
+            tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles, a[6] / tiles, a[7] / tiles);
+  }
   return 0;
 }
 
