@@ -29,15 +29,16 @@
 namespace disn {
 namespace {
 
-constexpr int NW = 6;                 // weight ring stages
+constexpr int NW = 3;                 // weight ring stages == weight producer warps (each owns one slot)
 constexpr int NX = 3;                 // activation (A operand) ring slots
 constexpr int NG = 2;                 // gather ring slots
-constexpr int W_STAGE = 16384;        // 128 rows x 64 k x bf16
+constexpr int W_TILE = 16384;         // 128 rows x 64 k x bf16 (one B tile half)
+constexpr int W_STAGE = 2 * W_TILE;   // [W_hi | W_lo] for one (K-slice, N-block)
 constexpr int X_HALF = 8192;          // 64 rows x 64 k x bf16
 constexpr int G_LD = 65;              // padded point stride of the gather ring
 constexpr int PTS = 64;               // points per CTA per tile
 constexpr int NTHREADS = 384;
-constexpr int STAGES_PER_STREAM = 66; // 2 + 16 + 32 + 16 weight stages (pair-level, 32 KB each)
+constexpr int STAGES_PER_STREAM = 33; // 1 + 8 + 16 + 8 weight stages (pair-level, 64 KB each: 2 CTA halves x [hi|lo])
 // shared-memory table of small fp32 parameters per stream
 constexpr int SB_B2 = 0, SB_B3 = 256, SB_B4 = 768, SB_B5 = 1280, SB_W6 = 1536, SB_W1 = 1792, SB_B1 = 1984, SB_STRIDE = 2048;
 constexpr int XSLOTS_PER_STREAM = 20; // 4 + 8 + 8 activation slices drained from TMEM (layer-1 output has its own slot)
@@ -150,32 +151,28 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     }                                                   \
   } while (0)
 
-  if (warp == 0) {
-    // ===================== weight producer (bulk-copy engine) =====================
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ===================== weight producers (bulk-copy engine): three warps, one ring slot each =============
+    // An mbarrier op costs the issuing thread ~200 cycles, so one producer thread cannot feed the MMAs;
+    // slot pw is filled, (in the peer CTA) relayed to the leader, and refilled by the same warp.
+    static_assert(NW == 3, "one producer warp per ring slot");
+    const int pw = (warp == 0) ? 0 : warp - 1;
     if (lane == 0) {
-      uint32_t seq = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int g = 0; g < 2 * STAGES_PER_STREAM; ++g, ++seq) {
-          const int st = seq % NW;
-          tc::mbar_wait(&s.wempty[st], ((seq / NW) & 1) ^ 1);
-          tc::mbar_arrive_expect_tx(&s.wfull[st], W_STAGE);
-          tc::bulk_g2s(s.w[st], wpk + (size_t)g * (2 * W_STAGE) + (size_t)cta * W_STAGE, W_STAGE, &s.wfull[st]);
+      const uint32_t total_stages = (uint32_t)my_tiles * (2 * STAGES_PER_STREAM);
+      for (uint32_t g = pw; g < total_stages; g += NW) {
+        const uint32_t use = g / NW;
+        tc::mbar_wait(&s.wempty[pw], (use & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&s.wfull[pw], W_STAGE);
+        tc::bulk_g2s(s.w[pw], wpk + (size_t)(g % (2 * STAGES_PER_STREAM)) * (2 * W_STAGE) + (size_t)cta * W_STAGE,
+                     W_STAGE, &s.wfull[pw]);
+        if (cta == 1) {      // leader's wfull counts {own expect_tx, this arrive}
+          tc::mbar_wait(&s.wfull[pw], use & 1);
+          tc::mbar_arrive_cluster(&s.wfull[pw], 0);
         }
       }
     }
   } else if (warp == 1) {
-    if (cta == 1) {
-      // ===================== relay: this CTA's half of a weight stage has landed -> tell the leader ==========
-      if (lane == 0) {
-        uint32_t seq = 0;
-        for (int it = 0; it < my_tiles; ++it)
-          for (int g = 0; g < 2 * STAGES_PER_STREAM; ++g, ++seq) {
-            const int st = seq % NW;
-            tc::mbar_wait(&s.wfull[st], (seq / NW) & 1);
-            tc::mbar_arrive_cluster(&s.wfull[st], 0);      // leader's wfull counts {own expect_tx, this arrive}
-          }
-      }
-    } else {
+    if (cta == 0) {
       // ===================== MMA issuer (leader CTA) =====================
       // The whole warp runs the loop so every address/descriptor is warp-uniform (uniform registers);
       // a single elected lane issues the tcgen05 instructions.
@@ -211,28 +208,18 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
 #pragma unroll 1
               for (int nb = 0; nb < nnb; ++nb) {
                 const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
-                // ---- stage "hi": A_hi*W_hi and A_lo*W_hi ----
-                int st = wseq % NW;
+                const int st = wseq % NW;
                 TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1));
                 tc::tc_fence_after_sync();
-                uint32_t b = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
+                const uint32_t b_hi = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
+                const uint32_t b_lo = b_hi + (W_TILE >> 4);
                 if (tc::elect_one()) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b + 2u * k, idesc, (t | k) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_lo + 2u * k, b + 2u * k, idesc, 1u);
-                  tc::commit_cg2(&s.wempty[st], 0b11);
-                }
-                __syncwarp();
-                ++wseq;
-                // ---- stage "lo": A_hi*W_lo ----
-                st = wseq % NW;
-                TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1));
-                tc::tc_fence_after_sync();
-                b = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
-                if (tc::elect_one()) {
+                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_lo + 2u * k, b_hi + 2u * k, idesc, 1u);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b + 2u * k, idesc, 1u);
+                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
                   tc::commit_cg2(&s.wempty[st], 0b11);
                 }
                 __syncwarp();
@@ -501,7 +488,7 @@ inline int fin_of(int layer, int t, int k) {
 }  // namespace
 
 // Pack both streams' tensor-core layers into the kernel's B-operand stage images:
-//   for stream, layer, slice t, N-block nb, part (hi, lo), CTA half c : 16 KB [128 rows n][64 k] SW128 bf16
+//   for stream, layer, slice t, N-block nb : CTA half c : part (hi, lo) : 16 KB [128 rows n][64 k] SW128 bf16
 int tc_pack_weights(disn_ctx* c) {
   static const int Ks[4] = {64, 256, 512, 512}, Ns[4] = {256, 512, 512, 256};
   const size_t total = (size_t)2 * STAGES_PER_STREAM * 2 * W_STAGE;
@@ -517,10 +504,10 @@ int tc_pack_weights(disn_ctx* c) {
       std::vector<float> w((size_t)K * N);   // rows 0..K-1 of the [Cin,Cout] matrix (point-feature part)
       DISN_CUDA_OK(cudaMemcpy(w.data(), it->second.ptr, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
       for (int t = 0; t < K / 64; ++t)
-        for (int nb = 0; nb < N / 256; ++nb)
-          for (int part = 0; part < 2; ++part, ++stage)
+        for (int nb = 0; nb < N / 256; ++nb, ++stage)
+          for (int part = 0; part < 2; ++part)
             for (int half = 0; half < 2; ++half) {
-              uint8_t* dst = img.data() + stage * (2 * W_STAGE) + (size_t)half * W_STAGE;
+              uint8_t* dst = img.data() + stage * (2 * W_STAGE) + (size_t)half * W_STAGE + (size_t)part * W_TILE;
               for (int nl = 0; nl < 128; ++nl) {
                 const int n = nb * 256 + half * 128 + nl;
                 for (int k = 0; k < 64; ++k) {

@@ -74,20 +74,34 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 #define DISN_MBAR_TIMEOUT_NS 4000000000ull   // 4 s: far beyond any legitimate wait in these kernels
 #endif
 // Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > DISN_MBAR_TIMEOUT_NS) __trap();
+// The timer is consulted only every 4096 failed polls: reading %globaltimer costs hundreds of cycles and
+// must stay off the common path (try_wait itself suspends the thread until the phase flips or a HW time slice).
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+  uint64_t t0 = 0;
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 0xFFFu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > DISN_MBAR_TIMEOUT_NS) __trap();
+    }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > DISN_MBAR_TIMEOUT_NS) __trap();
+    if ((++spins & 0xFFFu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > DISN_MBAR_TIMEOUT_NS) __trap();
+    }
   }
 }
 

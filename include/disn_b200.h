@@ -118,6 +118,10 @@ int disn_marching_cubes(disn_ctx* ctx, const float* sdf, int32_t R, const double
  * accumulated; returns the raw TMEM image D_out[2 CTAs][128 lanes][128 columns]. Host pointers. */
 int disn_tc_selftest(int device, const float* A, const float* B, int passes, float* D_out);
 
+/* Diagnostic: prints the achievable L2 -> shared-memory bulk-copy streaming rate (bytes/clk/SM) for a sweep of
+ * ring depths, stage sizes and cluster multicast widths (the weight-streaming pattern of the tensor-core kernel). */
+int disn_tc_stream_probe(int device);
+
 /* Kernel launch counter (bench's gpu_launches): number of this library's kernels launched so far. */
 int64_t disn_launch_count(disn_ctx* ctx);
 
