@@ -261,7 +261,6 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into activation slice `seq`
     auto drain = [&](uint32_t col0, int t, const float* bias, uint32_t seq, bool gather) {
       const int slot = seq % NX;
-      TIMED_WAIT(3, tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1));
       uint32_t r[32];
       tc::tmem_ld_x32(tlane + col0 + 32u * t, r);
       const int f0 = fout(h, 32 * t);
@@ -271,21 +270,23 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         const float4 bq = *reinterpret_cast<const float4*>(bias + f0 + j);
         v[j] = bq.x; v[j + 1] = bq.y; v[j + 2] = bq.z; v[j + 3] = bq.w;
       }
+      int gs = 0;
       if (gather) {
-        const int gs = gseq % NG;
+        gs = gseq % NG;
         TIMED_WAIT(5, tc::mbar_wait(&s.gfull[gs], (gseq / NG) & 1));
         const float* gp = s.g[gs] + (h * 32) * G_LD + p;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += gp[j * G_LD];
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&s.gempty[gs]);
         ++gseq;
       }
       tc::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + v[j], 0.f);
+      // the slot is only needed now: its release (MMA consumption of slice seq-NX) overlaps the work above
+      TIMED_WAIT(3, tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1));
       store_slice(s.x[slot][0], s.x[slot][1], p, h, v);
       arrive_xfull(slot);
+      if (gather && lane == 0) tc::mbar_arrive(&s.gempty[gs]);   // after the critical-path signal
     };
 
     for (int it = 0; it < my_tiles; ++it) {

@@ -40,7 +40,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // arrive on the barrier at the same smem offset in CTA `cta_rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) {
   uint32_t remote = mapa(smem_u32(bar), cta_rank);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // default semantics (.release at .cta scope), as CUTLASS's ClusterBarrier::arrive(cta_id): the signalled data is
+  // consumed by this CTA's own async proxy (tensor core reading this CTA's smem), already ordered by fence.proxy.async
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
