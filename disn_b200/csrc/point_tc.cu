@@ -138,7 +138,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
   tc::tc_fence_after_sync();
   const uint32_t tmem = s.tmem_base;
   // optional wait-time accounting (DISN_TC_TRACE=1): cycles each role spends blocked on each barrier class
-  unsigned long long wt[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long wt[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [6 + sidx*4 + layer]: MMA warp's activation waits
   const long long t_role0 = dbg ? clock64() : 0;
 #define TIMED_WAIT(slot, call)                          \
   do {                                                  \
@@ -181,6 +181,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       const uint32_t x_lo0 = tc::desc_lo(tc::smem_u32(s.x[0][0]));       // + slot * (2*X_HALF >> 4), lo = + X_HALF >> 4
       const uint32_t x2_lo0 = tc::desc_lo(tc::smem_u32(s.x2[0]));
       uint32_t wseq = 0, xseq = 0, nstream = 0;
+      bool w_ready = false;      // weights of unit `wseq` already waited for (look-ahead)
+      bool x_ready = false;      // activation slice `xseq` already waited for (look-ahead)
       for (int it = 0; it < my_tiles; ++it) {
         for (int sidx = 0; sidx < 2; ++sidx, ++nstream) {
 #pragma unroll 1
@@ -197,10 +199,11 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
               const int slot = xseq % NX;
               uint32_t a_hi;
               if (layer == 0) {      // A operand = layer-1 output staged by the front end
-                TIMED_WAIT(1, tc::mbar_wait(&s.x2full, nstream & 1));
+                TIMED_WAIT(6 + sidx * 4 + layer, tc::mbar_wait(&s.x2full, nstream & 1));
                 a_hi = x2_lo0;
               } else {
-                TIMED_WAIT(1, tc::mbar_wait(&s.xfull[slot], (xseq / NX) & 1));
+                if (!x_ready) TIMED_WAIT(6 + sidx * 4 + layer, tc::mbar_wait(&s.xfull[slot], (xseq / NX) & 1));
+                x_ready = false;
                 a_hi = x_lo0 + (uint32_t)slot * ((2 * X_HALF) >> 4);
               }
               const uint32_t a_lo = a_hi + (X_HALF >> 4);
@@ -209,7 +212,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
               for (int nb = 0; nb < nnb; ++nb) {
                 const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
                 const int st = wseq % NW;
-                TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1));
+                if (!w_ready) TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1));
+                w_ready = false;
                 tc::tc_fence_after_sync();
                 const uint32_t b_hi = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
                 const uint32_t b_lo = b_hi + (W_TILE >> 4);
@@ -239,7 +243,10 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       }
       if (dbg && lane == 0) {
         unsigned long long* o = dbg + (size_t)blockIdx.x * 16;
-        o[0] = (unsigned long long)(clock64() - t_role0); o[1] = wt[0]; o[2] = wt[1]; o[3] = wt[2];
+        o[0] = (unsigned long long)(clock64() - t_role0); o[1] = wt[0]; o[3] = wt[2];
+        unsigned long long act = 0;
+        for (int k = 0; k < 8; ++k) { o[8 + k] = wt[6 + k]; act += wt[6 + k]; }
+        o[2] = act;
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -445,27 +452,37 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         tc::mbar_wait(&s.gempty[gs], ((gsq / NG) & 1) ^ 1);
         float* gdst = s.g[gs];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int pt = fw * 16 + i * 4 + grp;
-          int off[4];
-          float wg[4];
+        for (int i2 = 0; i2 < 4; i2 += 2) {       // two point groups at a time: 16 x 16 B loads in flight per lane
+          float4 m[2][2][4];
+          float wg[2][4];
+          int pts[2];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { off[k] = s.tap_off[pt][k]; wg[k] = s.tap_w[pt][k]; }
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int fb = fout(hh, 32 * t) + q * 4;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < 2; ++u) {
+            const int pt = fw * 16 + (i2 + u) * 4 + grp;
+            pts[u] = pt;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (off[k] >= 0) {
-                const float4 m = __ldg(reinterpret_cast<const float4*>(pm + off[k] + fb));
-                a.x = fmaf(wg[k], m.x, a.x); a.y = fmaf(wg[k], m.y, a.y);
-                a.z = fmaf(wg[k], m.z, a.z); a.w = fmaf(wg[k], m.w, a.w);
-              }
+              const int off = s.tap_off[pt][k];
+              wg[u][k] = s.tap_w[pt][k];          // zero for taps outside the map
+              const float* src = pm + (off >= 0 ? off : 0);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh)
+                m[u][hh][k] = __ldg(reinterpret_cast<const float4*>(src + fout(hh, 32 * t) + q * 4));
             }
-            float* d = gdst + (hh * 32 + q * 4) * G_LD + pt;
-            d[0] = a.x; d[G_LD] = a.y; d[2 * G_LD] = a.z; d[3 * G_LD] = a.w;
           }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                a.x = fmaf(wg[u][k], m[u][hh][k].x, a.x); a.y = fmaf(wg[u][k], m[u][hh][k].y, a.y);
+                a.z = fmaf(wg[u][k], m[u][hh][k].z, a.z); a.w = fmaf(wg[u][k], m[u][hh][k].w, a.w);
+              }
+              float* d = gdst + (hh * 32 + q * 4) * G_LD + pts[u];
+              d[0] = a.x; d[G_LD] = a.y; d[2 * G_LD] = a.z; d[3 * G_LD] = a.w;
+            }
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s.gfull[gs]);
@@ -570,6 +587,11 @@ int launch_point_tc(disn_ctx* c, const PointJob& job) {
     fprintf(stderr, "[DISN_TC_TRACE] tiles/pair=%.1f  per-tile cycles: MMA warp total=%.0f wait{weights=%.0f, act=%.0f, acc5=%.0f} | "
                     "epilogue warp total=%.0f wait{xempty=%.0f, acc_full=%.0f, gather=%.0f}\n",
             tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles, a[6] / tiles, a[7] / tiles);
+    double lw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < pairs; ++p)
+      for (int k = 0; k < 8; ++k) lw[k] += (double)h[(size_t)(2 * p) * 16 + 8 + k] / pairs / tiles;
+    fprintf(stderr, "[DISN_TC_TRACE] MMA warp activation waits per tile: global L2..L5 = %.0f %.0f %.0f %.0f | local L2..L5 = %.0f %.0f %.0f %.0f\n",
+            lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
   }
   return 0;
 }
