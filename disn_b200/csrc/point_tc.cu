@@ -157,18 +157,23 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     // slot pw is filled, (in the peer CTA) relayed to the leader, and refilled by the same warp.
     static_assert(NW == 3, "one producer warp per ring slot");
     const int pw = (warp == 0) ? 0 : warp - 1;
-    if (lane == 0) {
+    if (lane < 2) {          // two lanes issue one 16 KB tile each (hi / lo) so the copies overlap
       const uint32_t total_stages = (uint32_t)my_tiles * (2 * STAGES_PER_STREAM);
+      if (lane == 0 && (uint32_t)pw < total_stages) tc::mbar_arrive_expect_tx(&s.wfull[pw], W_STAGE);
+      __syncwarp(0x3);
       for (uint32_t g = pw; g < total_stages; g += NW) {
         const uint32_t use = g / NW;
         tc::mbar_wait(&s.wempty[pw], (use & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(&s.wfull[pw], W_STAGE);
-        tc::bulk_g2s(s.w[pw], wpk + (size_t)(g % (2 * STAGES_PER_STREAM)) * (2 * W_STAGE) + (size_t)cta * W_STAGE,
-                     W_STAGE, &s.wfull[pw]);
-        if (cta == 1) {      // leader's wfull counts {own expect_tx, this arrive}
-          tc::mbar_wait(&s.wfull[pw], use & 1);
-          tc::mbar_arrive_cluster(&s.wfull[pw], 0);
+        const uint8_t* src = wpk + (size_t)(g % (2 * STAGES_PER_STREAM)) * (2 * W_STAGE) + (size_t)cta * W_STAGE +
+                             (size_t)lane * W_TILE;
+        tc::bulk_g2s(s.w[pw] + lane * W_TILE, src, W_TILE, &s.wfull[pw]);
+        tc::mbar_wait(&s.wfull[pw], use & 1);     // leader: own bytes + peer relay; peer: own bytes
+        if (lane == 0) {
+          if (cta == 1) tc::mbar_arrive_cluster(&s.wfull[pw], 0);   // leader's wfull counts {own expect_tx, this arrive}
+          // pre-post the next use's transaction count so that only the copy issue follows the slot release
+          if (g + NW < total_stages) tc::mbar_arrive_expect_tx(&s.wfull[pw], W_STAGE);
         }
+        __syncwarp(0x3);
       }
     }
   } else if (warp == 1) {
@@ -181,7 +186,6 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       const uint32_t x_lo0 = tc::desc_lo(tc::smem_u32(s.x[0][0]));       // + slot * (2*X_HALF >> 4), lo = + X_HALF >> 4
       const uint32_t x2_lo0 = tc::desc_lo(tc::smem_u32(s.x2[0]));
       uint32_t wseq = 0, xseq = 0, nstream = 0;
-      bool w_ready = false;      // weights of unit `wseq` already waited for (look-ahead)
       bool x_ready = false;      // activation slice `xseq` already waited for (look-ahead)
       for (int it = 0; it < my_tiles; ++it) {
         for (int sidx = 0; sidx < 2; ++sidx, ++nstream) {
@@ -212,11 +216,11 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
               for (int nb = 0; nb < nnb; ++nb) {
                 const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
                 const int st = wseq % NW;
-                if (!w_ready) TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1));
-                w_ready = false;
+                TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1));
                 tc::tc_fence_after_sync();
                 const uint32_t b_hi = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
                 const uint32_t b_lo = b_hi + (W_TILE >> 4);
+                const long long ti = dbg ? clock64() : 0;
                 if (tc::elect_one()) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
@@ -227,6 +231,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                   tc::commit_cg2(&s.wempty[st], 0b11);
                 }
                 __syncwarp();
+                if (dbg) wt[1] += (unsigned long long)(clock64() - ti);
                 ++wseq;
               }
               if (tc::elect_one()) {
@@ -246,7 +251,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         o[0] = (unsigned long long)(clock64() - t_role0); o[1] = wt[0]; o[3] = wt[2];
         unsigned long long act = 0;
         for (int k = 0; k < 8; ++k) { o[8 + k] = wt[6 + k]; act += wt[6 + k]; }
-        o[2] = act;
+        o[2] = act; o[4] = wt[1];
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -353,7 +358,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     }
     if (dbg && tid == 128) {
       unsigned long long* o = dbg + (size_t)blockIdx.x * 16;
-      o[4] = (unsigned long long)(clock64() - t_role0); o[5] = wt[3]; o[6] = wt[4]; o[7] = wt[5];
+      if (cta == 1) o[4] = (unsigned long long)(clock64() - t_role0);
+      o[5] = wt[3]; o[6] = wt[4]; o[7] = wt[5];
     }
   } else if (warp >= 8) {
     // ===================== front end: points, projection, layer 1, feature gather =====================
@@ -581,7 +587,8 @@ int launch_point_tc(disn_ctx* c, const PointJob& job) {
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = 0; p < pairs; ++p) {
       for (int k = 0; k < 4; ++k) a[k] += (double)h[(size_t)(2 * p) * 16 + k] / pairs;                 // leader's MMA warp
-      for (int k = 4; k < 8; ++k) a[k] += 0.5 * ((double)h[(size_t)(2 * p) * 16 + k] + (double)h[(size_t)(2 * p + 1) * 16 + k]) / pairs;
+      a[4] += (double)h[(size_t)(2 * p + 1) * 16 + 4] / pairs;                                          // peer epilogue total
+      for (int k = 5; k < 8; ++k) a[k] += 0.5 * ((double)h[(size_t)(2 * p) * 16 + k] + (double)h[(size_t)(2 * p + 1) * 16 + k]) / pairs;
     }
     const double tiles = (double)total / pairs;
     fprintf(stderr, "[DISN_TC_TRACE] tiles/pair=%.1f  per-tile cycles: MMA warp total=%.0f wait{weights=%.0f, act=%.0f, acc5=%.0f} | "
@@ -590,6 +597,9 @@ int launch_point_tc(disn_ctx* c, const PointJob& job) {
     double lw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = 0; p < pairs; ++p)
       for (int k = 0; k < 8; ++k) lw[k] += (double)h[(size_t)(2 * p) * 16 + 8 + k] / pairs / tiles;
+    double issue = 0;
+    for (int p = 0; p < pairs; ++p) issue += (double)h[(size_t)(2 * p) * 16 + 4] / pairs / tiles;
+    fprintf(stderr, "[DISN_TC_TRACE] MMA warp time inside the 12-MMA issue blocks per tile: %.0f cycles (66 blocks)\n", issue);
     fprintf(stderr, "[DISN_TC_TRACE] MMA warp activation waits per tile: global L2..L5 = %.0f %.0f %.0f %.0f | local L2..L5 = %.0f %.0f %.0f %.0f\n",
             lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
   }
