@@ -94,6 +94,7 @@ __device__ __forceinline__ void store_slice(uint8_t* xhi, uint8_t* xlo, int p, i
   }
 }
 
+template <bool kTrace>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per_img,
                 unsigned long long* __restrict__ dbg) {
@@ -139,10 +140,10 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
   const uint32_t tmem = s.tmem_base;
   // optional wait-time accounting (DISN_TC_TRACE=1): cycles each role spends blocked on each barrier class
   unsigned long long wt[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [6 + sidx*4 + layer]: MMA warp's activation waits
-  const long long t_role0 = dbg ? clock64() : 0;
+  const long long t_role0 = kTrace ? clock64() : 0;
 #define TIMED_WAIT(slot, call)                          \
   do {                                                  \
-    if (dbg) {                                          \
+    if constexpr (kTrace) {                             \
       const long long _t = clock64();                   \
       call;                                             \
       wt[slot] += (unsigned long long)(clock64() - _t); \
@@ -185,8 +186,9 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       const uint32_t w_lo0 = tc::desc_lo(tc::smem_u32(s.w[0]));          // + st * (W_STAGE >> 4)
       const uint32_t x_lo0 = tc::desc_lo(tc::smem_u32(s.x[0][0]));       // + slot * (2*X_HALF >> 4), lo = + X_HALF >> 4
       const uint32_t x2_lo0 = tc::desc_lo(tc::smem_u32(s.x2[0]));
-      uint32_t wseq = 0, xseq = 0, nstream = 0;
-      bool x_ready = false;      // activation slice `xseq` already waited for (look-ahead)
+      uint32_t xseq = 0, nstream = 0;
+      uint32_t wst = 0, wph = 0;      // weight ring slot / phase parity
+      uint32_t xsl = 0, xph = 0;      // activation ring slot / phase parity
       for (int it = 0; it < my_tiles; ++it) {
         for (int sidx = 0; sidx < 2; ++sidx, ++nstream) {
 #pragma unroll 1
@@ -200,14 +202,13 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
             }
 #pragma unroll 1
             for (int t = 0; t < nsl; ++t) {
-              const int slot = xseq % NX;
+              const uint32_t slot = xsl;
               uint32_t a_hi;
               if (layer == 0) {      // A operand = layer-1 output staged by the front end
                 TIMED_WAIT(6 + sidx * 4 + layer, tc::mbar_wait(&s.x2full, nstream & 1));
                 a_hi = x2_lo0;
               } else {
-                if (!x_ready) TIMED_WAIT(6 + sidx * 4 + layer, tc::mbar_wait(&s.xfull[slot], (xseq / NX) & 1));
-                x_ready = false;
+                TIMED_WAIT(6 + sidx * 4 + layer, tc::mbar_wait(&s.xfull[slot], xph));
                 a_hi = x_lo0 + (uint32_t)slot * ((2 * X_HALF) >> 4);
               }
               const uint32_t a_lo = a_hi + (X_HALF >> 4);
@@ -215,12 +216,12 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
 #pragma unroll 1
               for (int nb = 0; nb < nnb; ++nb) {
                 const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
-                const int st = wseq % NW;
-                TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], (wseq / NW) & 1));
+                const uint32_t st = wst;
+                TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], wph));
                 tc::tc_fence_after_sync();
                 const uint32_t b_hi = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
                 const uint32_t b_lo = b_hi + (W_TILE >> 4);
-                const long long ti = dbg ? clock64() : 0;
+                const long long ti = kTrace ? clock64() : 0;
                 if (tc::elect_one()) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
@@ -231,22 +232,22 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                   tc::commit_cg2(&s.wempty[st], 0b11);
                 }
                 __syncwarp();
-                if (dbg) wt[1] += (unsigned long long)(clock64() - ti);
-                ++wseq;
+                if constexpr (kTrace) wt[1] += (unsigned long long)(clock64() - ti);
+                if (++wst == NW) { wst = 0; wph ^= 1u; }
               }
               if (tc::elect_one()) {
                 if (layer == 0) tc::commit_cg2(&s.x2empty, 0b11);
                 else tc::commit_cg2(&s.xempty[slot], 0b11);
               }
               __syncwarp();
-              if (layer != 0) ++xseq;
+              if (layer != 0) { ++xseq; if (++xsl == NX) { xsl = 0; xph ^= 1u; } }
             }
             if (tc::elect_one()) tc::commit_cg2(&s.acc_full[layer], 0b11);
             __syncwarp();
           }
         }
       }
-      if (dbg && lane == 0) {
+      if (kTrace && lane == 0) {
         unsigned long long* o = dbg + (size_t)blockIdx.x * 16;
         o[0] = (unsigned long long)(clock64() - t_role0); o[1] = wt[0]; o[3] = wt[2];
         unsigned long long act = 0;
@@ -356,7 +357,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         }
       }
     }
-    if (dbg && tid == 128) {
+    if (kTrace && tid == 128) {
       unsigned long long* o = dbg + (size_t)blockIdx.x * 16;
       if (cta == 1) o[4] = (unsigned long long)(clock64() - t_role0);
       o[5] = wt[3]; o[6] = wt[4]; o[7] = wt[5];
@@ -560,7 +561,8 @@ int launch_point_tc(disn_ctx* c, const PointJob& job) {
   static bool attr_set = false;
   const int smem = (int)sizeof(TcSmem) + 1024;
   if (!attr_set) {
-    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int64_t tiles_per_img = (job.N + 2 * PTS - 1) / (2 * PTS);
@@ -575,8 +577,12 @@ int launch_point_tc(disn_ctx* c, const PointJob& job) {
     DISN_CUDA_OK(cudaMalloc(&dbg, (size_t)pairs * 2 * 16 * sizeof(unsigned long long)));
     DISN_CUDA_OK(cudaMemsetAsync(dbg, 0, (size_t)pairs * 2 * 16 * sizeof(unsigned long long), c->stream));
   }
-  point_tc_kernel<<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(c->tc_weights),
-                                                           tiles_per_img, dbg);
+  if (trace)
+    point_tc_kernel<true><<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(c->tc_weights),
+                                                                  tiles_per_img, dbg);
+  else
+    point_tc_kernel<false><<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(c->tc_weights),
+                                                                   tiles_per_img, dbg);
   c->launches++;
   DISN_CUDA_OK(cudaGetLastError());
   if (trace) {   // debug only: per-role blocked cycles, averaged over CTAs

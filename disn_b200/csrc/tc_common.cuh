@@ -90,9 +90,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#pragma unroll 1
-  for (int i = 0; i < 64; ++i)
-    if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;      // try_wait itself suspends for a HW time slice when not ready
   mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
