@@ -329,6 +329,32 @@ int disn_write_dist(const char* path, int32_t res, const double* bbox, const flo
   return 0;
 }
 
+int disn_nn_distance(disn_ctx* c, const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, float* dist1,
+                     int32_t* idx1, float* dist2, int32_t* idx2) {
+  DISN_REQUIRE(c && xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "null argument");
+  DISN_REQUIRE(B >= 1 && N >= 1 && M >= 1, "NnDistance requires non-empty point sets of shape (batch,#points,3)");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  float *d1 = nullptr, *d2 = nullptr, *o1 = nullptr, *o2 = nullptr;
+  int *i1 = nullptr, *i2 = nullptr;
+  auto cleanup = [&]() { cudaFree(d1); cudaFree(d2); cudaFree(o1); cudaFree(o2); cudaFree(i1); cudaFree(i2); };
+  cudaError_t e;
+#define NN_OK(expr) if ((e = (expr)) != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e)); cleanup(); return -1; }
+  NN_OK(cudaMalloc(&d1, (size_t)B * N * 3 * 4)); NN_OK(cudaMalloc(&d2, (size_t)B * M * 3 * 4));
+  NN_OK(cudaMalloc(&o1, (size_t)B * N * 4)); NN_OK(cudaMalloc(&o2, (size_t)B * M * 4));
+  NN_OK(cudaMalloc(&i1, (size_t)B * N * 4)); NN_OK(cudaMalloc(&i2, (size_t)B * M * 4));
+  NN_OK(cudaMemcpyAsync(d1, xyz1, (size_t)B * N * 3 * 4, cudaMemcpyHostToDevice, c->stream));
+  NN_OK(cudaMemcpyAsync(d2, xyz2, (size_t)B * M * 3 * 4, cudaMemcpyHostToDevice, c->stream));
+  if (nn_distance(c, d1, N, d2, M, B, o1, i1, o2, i2)) { cleanup(); return -1; }
+  NN_OK(cudaMemcpyAsync(dist1, o1, (size_t)B * N * 4, cudaMemcpyDeviceToHost, c->stream));
+  NN_OK(cudaMemcpyAsync(idx1, i1, (size_t)B * N * 4, cudaMemcpyDeviceToHost, c->stream));
+  NN_OK(cudaMemcpyAsync(dist2, o2, (size_t)B * M * 4, cudaMemcpyDeviceToHost, c->stream));
+  NN_OK(cudaMemcpyAsync(idx2, i2, (size_t)B * M * 4, cudaMemcpyDeviceToHost, c->stream));
+  NN_OK(cudaStreamSynchronize(c->stream));
+#undef NN_OK
+  cleanup();
+  return 0;
+}
+
 int disn_write_obj(const char* path, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces) {
   DISN_REQUIRE(path && (verts || n_verts == 0) && (faces || n_faces == 0) && n_verts >= 0 && n_faces >= 0,
                "bad write_obj arguments");

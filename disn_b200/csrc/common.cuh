@@ -128,6 +128,9 @@ int launch_point_fp32(disn_ctx* c, const PointJob& job);
 // point_tc.cu
 int tc_pack_weights(disn_ctx* c);
 int launch_point_tc(disn_ctx* c, const PointJob& job);
+// chamfer.cu
+int nn_distance(disn_ctx* c, const float* d_xyz1, int n, const float* d_xyz2, int m, int B, float* d_dist1,
+                int* d_idx1, float* d_dist2, int* d_idx2);
 // mc.cu
 int marching_cubes(disn_ctx* c, const float* d_sdf, int R, const double* bbox, float iso,
                    float* verts, int64_t* n_verts, int32_t* faces, int64_t* n_faces, bool count_only);

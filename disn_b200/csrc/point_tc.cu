@@ -12,12 +12,16 @@
 //   * activations never leave the SM: layer l's accumulator is drained 32 columns at a time by the
 //     epilogue warps (bias / folded image features, ReLU, bf16 hi/lo split) into a 3-slot ring of
 //     K-major 128B-swizzled A tiles that layer l+1's MMAs consume (K-outer), so MMA and epilogue pipeline;
-//   * weights are pre-split, pre-permuted and pre-swizzled on the host into the exact 16 KB shared-memory
-//     images the B operand needs and streamed by the bulk-copy engine (cp.async.bulk) through a 6-stage
-//     mbarrier ring; each CTA loads only its half of every B tile;
-//   * warp roles: 0 weight producer, 1 MMA issuer (leader CTA) / full-barrier relay (peer CTA),
-//     2 TMEM allocator, 4-7 epilogue (one TMEM lane each), 8-11 front end (points, projection, layer 1,
-//     bilinear gather of the projected feature map into a shared-memory ring).
+//   * weights are pre-split, pre-permuted and pre-swizzled on the host into the exact shared-memory images the
+//     B operand needs ([W_hi | W_lo] = 32 KB per (K-slice, N-block) and CTA) and streamed by the bulk-copy engine
+//     (cp.async.bulk) through a 3-slot mbarrier ring; each CTA loads only its half of every B tile, the peer
+//     relays its arrival to the leader.  An mbarrier operation costs the issuing thread ~200 cycles, so each
+//     ring slot has its own producer warp and the stage is as large as shared memory allows;
+//   * warp roles: 0,2,3 weight producers (2 also allocates TMEM), 1 MMA issuer (leader CTA; warp-uniform loop,
+//     one elected lane issues), 4-7 epilogue (one TMEM lane each), 8-11 front end (points, projection,
+//     layer 1, bilinear gather of the projected feature map into a shared-memory ring);
+//   * DISN_TC_TRACE=1 runs an instrumented instantiation that accounts the cycles every role spends blocked
+//     on each barrier class (profiles/*_tc_wait_trace.txt).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -144,6 +144,24 @@ class Engine:
         check(self.lib.disn_eval_grid(self._h, sp.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(trans_mat_ptr),
                                       sp.shape[0], sdf_res, z0, z1, C.c_void_p(out_ptr), DISN_DEVICE_PTR))
 
+    # -- mesh metrics -------------------------------------------------------------------------
+    def nn_distance(self, xyz1, xyz2):
+        """The reference's tf_nndistance.nn_distance(xyz1, xyz2): squared NN distances + indices, both ways."""
+        a, b = _f32(xyz1), _f32(xyz2)
+        B, N, _ = a.shape
+        M = b.shape[1]
+        d1, i1 = np.empty((B, N), np.float32), np.empty((B, N), np.int32)
+        d2, i2 = np.empty((B, M), np.float32), np.empty((B, M), np.int32)
+        check(self.lib.disn_nn_distance(self._h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), B, N, M,
+                                        d1.ctypes.data_as(C.c_void_p), i1.ctypes.data_as(C.c_void_p),
+                                        d2.ctypes.data_as(C.c_void_p), i2.ctypes.data_as(C.c_void_p)))
+        return d1, i1, d2, i2
+
+    def chamfer_x1000(self, pred, src):
+        """test/test_cd_emd.py:300-301: (mean forward + mean backward squared NN distance) * 1000, per batch item."""
+        df, _, db, _ = self.nn_distance(pred, src)
+        return (df.mean(axis=1) + db.mean(axis=1)) * np.float32(1000)
+
     # -- marching cubes -----------------------------------------------------------------------
     def marching_cubes(self, sdf, bbox, iso: float = 0.0, device_ptr: int | None = None, R: int | None = None):
         """sdf [R,R,R] (z,y,x) -> (verts [V,3] float32, faces [F,3] int32 0-based)."""

@@ -114,6 +114,13 @@ int disn_write_obj(const char* path, const float* verts, int64_t n_verts, const 
 int disn_marching_cubes(disn_ctx* ctx, const float* sdf, int32_t R, const double* bbox, float iso,
                         float* verts, int64_t* n_verts, int32_t* faces, int64_t* n_faces, uint32_t flags);
 
+/* Chamfer nearest-neighbour distances, the reference's NnDistance op (models/tf_ops/nn_distance/tf_nndistance.cpp:
+ * 21-43; called at test/test_cd_emd.py:300, test/test_f_score.py:253): xyz1 [B,N,3], xyz2 [B,M,3] host float32 ->
+ * dist1 [B,N] (squared L2 to the nearest point of xyz2), idx1 [B,N] int32, dist2 [B,M], idx2 [B,M].
+ * Bit-identical to the reference CPU kernel (float32 arithmetic, first minimum wins). */
+int disn_nn_distance(disn_ctx* ctx, const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M,
+                     float* dist1, int32_t* idx1, float* dist2, int32_t* idx2);
+
 /* Diagnostic: one CTA-pair tcgen05 (cta_group::2) GEMM D[128x256] = A[128x64] * B[256x64]^T, `passes` times
  * accumulated; returns the raw TMEM image D_out[2 CTAs][128 lanes][128 columns]. Host pointers. */
 int disn_tc_selftest(int device, const float* A, const float* B, int passes, float* D_out);

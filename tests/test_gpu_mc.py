@@ -48,3 +48,26 @@ def test_mesh_of_predicted_grid_is_consistent(engine, he_weights):
     assert len(f) > 100
     np.testing.assert_array_equal(f, rf)
     np.testing.assert_array_equal(v, rv)
+
+
+def test_nn_distance_bit_exact_vs_reference_op(engine):
+    """CUDA NnDistance == the CPU oracle == the reference's own compiled op (when oracle/_ref was built):
+    shapes of the reference call site (test/test_cd_emd.py:42-45: [views,2048,3])."""
+    from oracle import metrics_oracle as mo
+    rng = np.random.default_rng(7)
+    a = rng.uniform(-1, 1, (4, 2048, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, (4, 1500, 3)).astype(np.float32)
+    b[2, 10] = b[2, 700]                                    # exact tie -> first index wins
+    got = engine.nn_distance(a, b)
+    ref = mo.nn_distance(a, b)
+    for g, r in zip(got, ref):
+        np.testing.assert_array_equal(g, r)
+    try:
+        for g, r in zip(got, mo.ref_nn_distance(a, b)):
+            np.testing.assert_array_equal(g, r)
+    except FileNotFoundError:
+        pass
+    np.testing.assert_allclose(engine.chamfer_x1000(a, b), mo.chamfer_x1000(a, b), rtol=1e-6)
+    from disn_b200._lib import DisnError
+    with pytest.raises(DisnError):
+        engine.nn_distance(a[:, :0], b)                     # empty set: loud error like the op's shape checks

@@ -87,3 +87,47 @@ def test_tc_grid_matches_fp32_path_and_slabs(tc_engine):
     a = tc_engine.eval_grid(sp, tm, 40, z0=0, z1=17)
     b = tc_engine.eval_grid(sp, tm, 40, z0=17, z1=41)
     np.testing.assert_array_equal(np.concatenate([a, b], axis=1), g_tc)   # deterministic, slab-invariant
+
+
+def test_full_size_grid_properties(tc_engine):
+    """BASELINE config 1 at full size (257^3 = 16 974 593 points): size-independent properties instead of the
+    CPU oracle -- (i) tensor-core path within 1e-4 of the fp32 CUDA-core path everywhere, (ii) bitwise
+    run-to-run determinism, (iii) z-slab sharding (the multi-GPU decomposition) reproduces the single call."""
+    from disn_b200 import synth
+    imgs = synth.synthetic_images(1)
+    tc_engine.encode(imgs)
+    tm, sp = synth.DEMO_TRANS_MAT, synth.DEMO_SDF_PARAMS
+    g1 = tc_engine.eval_grid(sp, tm, 256)
+    assert g1.shape == (1, 257, 257, 257) and np.isfinite(g1).all()
+    g2 = tc_engine.eval_grid(sp, tm, 256)
+    np.testing.assert_array_equal(g1, g2)
+    slabs = [tc_engine.eval_grid(sp, tm, 256, z0=a, z1=b) for a, b in ((0, 32), (32, 129), (129, 257))]
+    np.testing.assert_array_equal(np.concatenate(slabs, axis=1), g1)
+    tc_engine.set_precision("fp32")
+    g32 = tc_engine.eval_grid(sp, tm, 256)
+    tc_engine.set_precision("bf16x3")
+    err = float(np.abs(g1 - g32).max())
+    rms = float(np.sqrt(np.mean(g32.astype(np.float64) ** 2)))
+    assert err <= 1e-4, (err, rms)
+    assert rms > 0.02
+
+
+def test_batch_of_eight_images(he_weights):
+    """BASELINE config 2 shape: batch = 8 images through one encode + one grid call; spot-check two of them."""
+    from disn_b200 import synth
+    from disn_b200.engine import Engine
+    from oracle import disn_oracle as orc
+    eng = Engine(device=0, precision="bf16x3", max_batch=8)
+    try:
+        eng.load_weights(he_weights)
+        imgs = synth.synthetic_images(8, seed=500)
+        tms = synth.synthetic_trans_mats(8, seed=600)
+        sps = np.tile(synth.DEMO_SDF_PARAMS, (8, 1))
+        eng.encode(imgs)
+        grid = eng.eval_grid(sps, tms, 10)
+        assert grid.shape == (8, 11, 11, 11)
+        for b in (0, 7):
+            ref = orc.create_sdf_grid(imgs[b:b + 1], tms[b:b + 1], sps[b:b + 1], he_weights, sdf_res=10, dtype=np.float64)
+            assert np.abs(grid[b].reshape(-1) - ref.reshape(-1)).max() <= 1e-4
+    finally:
+        eng.close()

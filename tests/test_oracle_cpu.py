@@ -95,3 +95,28 @@ def test_get_loss_metrics():
     m = orc.get_loss(pred, gt)
     assert abs(m["accuracy"] - 2 / 3) < 1e-6
     assert abs(m["sdf_loss_realvalue"] - np.mean([0.0, 0.1, 0.1])) < 1e-6
+
+
+def test_nn_distance_oracle_matches_reference_compiled_op():
+    """oracle/metrics_oracle.nn_distance == the reference's own CPU op compiled in place (oracle/_ref)."""
+    import pytest
+    from oracle import metrics_oracle as mo
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((3, 257, 3)).astype(np.float32)
+    b = rng.standard_normal((3, 100, 3)).astype(np.float32)
+    b[1, 5] = b[1, 9]                       # exact tie: the first minimum must win
+    try:
+        ref = mo.ref_nn_distance(a, b)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    got = mo.nn_distance(a, b)
+    for g, r in zip(got, ref):
+        np.testing.assert_array_equal(g, r)
+    # 5x6 points, seed 0: the reference's own eyeball check (tf_nndistance_cpu.py:26-48 verify_nn_distance_cup)
+    np.random.seed(0)
+    x1 = np.random.randn(1, 5, 3).astype(np.float32)
+    x2 = np.random.randn(1, 6, 3).astype(np.float32)
+    d1, i1, d2, i2 = mo.nn_distance(x1, x2)
+    brute = ((x1[0][:, None] - x2[0][None]) ** 2).sum(-1)
+    np.testing.assert_allclose(d1[0], brute.min(1), rtol=1e-6)
+    np.testing.assert_array_equal(i1[0], brute.argmin(1))
