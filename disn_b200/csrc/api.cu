@@ -63,8 +63,9 @@ void disn_destroy(disn_ctx* c) {
   cudaStreamSynchronize(c->stream);
   encoder_free(c);
   for (auto& kv : c->weights) cudaFree(kv.second.ptr);
-  for (float* p : {c->d_pts, c->d_pts_rot, c->d_out, c->d_uv, c->d_tm, c->d_axes, c->tc_small})
+  for (float* p : {c->d_pts, c->d_pts_rot, c->d_out, c->d_uv, c->d_tm, c->d_axes})
     if (p) cudaFree(p);
+  for (auto& kv : c->enc_tc_weights) cudaFree(kv.second);
   if (c->tc_weights) cudaFree(c->tc_weights);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -117,6 +118,8 @@ int disn_load_weight(disn_ctx* c, const char* name, const float* data, const int
   t.numel = numel;
   DISN_CUDA_OK(cudaMemcpy(t.ptr, data, numel * sizeof(float), cudaMemcpyHostToDevice));
   c->weights_dirty = true;
+  for (auto& kv : c->enc_tc_weights) cudaFree(kv.second);     // packed encoder weights follow the fp32 masters
+  c->enc_tc_weights.clear();
   return 0;
 }
 

@@ -104,7 +104,6 @@ struct disn_ctx {
   float* emb = nullptr;         // [B,num_classes]
   float* gbias = nullptr;       // [B,512]
   float* pmap = nullptr;        // [B,img_h,img_w,512]
-  float* w_local_feat = nullptr;   // view into fold2/conv1 weights rows 512.. [1472,512]
   // scratch for host-pointer calls
   float* d_pts = nullptr; float* d_pts_rot = nullptr; float* d_out = nullptr; float* d_uv = nullptr;
   int64_t scratch_pts = 0;
@@ -115,7 +114,7 @@ struct disn_ctx {
   // bf16x3 packed weights (tcgen05 path)
   void* tc_weights = nullptr;
   int64_t tc_weights_bytes = 0;
-  float* tc_small = nullptr;    // fp32 small params for the tcgen05 kernel
+  std::map<std::string, uint8_t*> enc_tc_weights;   // packed bf16 hi/lo stage images of the encoder GEMMs
 };
 
 namespace disn {
@@ -128,6 +127,10 @@ int launch_point_fp32(disn_ctx* c, const PointJob& job);
 // point_tc.cu
 int tc_pack_weights(disn_ctx* c);
 int launch_point_tc(disn_ctx* c, const PointJob& job);
+// conv_tc.cu
+int conv_tc_pack(const float* d_w, int K, int N, uint8_t** out_dev);
+int launch_conv_tc(disn_ctx* c, const float* A, const uint8_t* wpk, const float* bias, float* C, float* ws,
+                   int64_t ws_elems, int M, int N, int K, int H, int W, int Cin, int relu, int* splits_out);
 // chamfer.cu
 int nn_distance(disn_ctx* c, const float* d_xyz1, int n, const float* d_xyz2, int m, int B, float* d_dist1,
                 int* d_idx1, float* d_dist2, int* d_idx2);

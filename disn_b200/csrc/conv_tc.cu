@@ -1,0 +1,308 @@
+// Implicit-GEMM convolution / GEMM on tcgen05 tensor cores for the image encoder (sm_100a).
+//
+//   C[M, N] = act( A[M, K] * W[K, N] + bias ),  A = NHWC activations viewed through a 3x3 SAME im2col
+//   (K = 9*Cin, k = tap*Cin + ci -- the row order of TF's HWIO weights) or a plain row-major matrix.
+//
+// Same precision scheme as the point kernel: every fp32 operand is split into bf16 hi + lo and each product is
+// three MMAs (hi*hi + lo*hi + hi*lo) with fp32 accumulation in TMEM, so the encoder keeps fp32-level accuracy
+// (the reference runs VGG in fp32; models/CNN/vgg.py:187-196, models/model_normalization.py:76).
+//
+// One CTA = one SM: UMMA M=128 (pixels) x N=128 (output channels) x K=16, 64-wide K slices.
+//   warps 8-15  A producers (two groups of 4 warps alternate slices): thread = one pixel row; gathers 64
+//               channels of one filter tap (256 contiguous bytes, or zeros outside the image), splits to
+//               bf16 hi/lo and writes the K-major 128B-swizzled A tile
+//   warp 0      B producer: host-packed [W_hi | W_lo] 32 KB stage images via cp.async.bulk
+//   warp 1      MMA issuer (warp-uniform loop, elected lane), two TMEM accumulators (ping-pong across jobs)
+//   warps 4-7   epilogue: TMEM -> +bias, ReLU -> fp32 NHWC store (or raw split-K partials to the workspace)
+// Jobs = (m-tile, n-block, k-split); a persistent grid walks them.  Under-filled layers are split along K and
+// reduced by splitk_reduce_kernel.
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace disn {
+namespace {
+
+constexpr int CT_THREADS = 512;
+constexpr int CT_NA = 4;            // A ring slots (2 per producer group)
+constexpr int CT_NB = 3;            // B ring slots
+constexpr int CT_A_HALF = 16384;    // 128 rows x 64 k x bf16
+constexpr int CT_B_TILE = 16384;    // 128 rows x 64 k x bf16
+constexpr int CT_B_STAGE = 2 * CT_B_TILE;
+
+struct ConvTcSmem {
+  alignas(1024) uint8_t a[CT_NA][2][CT_A_HALF];    // [slot][hi|lo]   128 KB
+  alignas(1024) uint8_t b[CT_NB][CT_B_STAGE];      // [slot][hi|lo]    96 KB
+  alignas(8) uint64_t afull[CT_NA];
+  uint64_t aempty[CT_NA];
+  uint64_t bfull[CT_NB];
+  uint64_t bempty[CT_NB];
+  uint64_t acc_full[2];
+  uint64_t acc_free[2];
+  uint32_t tmem_base;
+};
+
+struct ConvTcJob {
+  const float* A;          // NHWC activations [B,H,W,Cin] or row-major [M,K]
+  const uint8_t* wpk;      // packed weights: [n-block][k-slice][hi|lo][128 x 64 SW128]
+  const float* bias;       // [N] or nullptr
+  float* C;                // [M,N] fp32
+  float* ws;               // split-K workspace [splits][M][N] or nullptr
+  int M, N, K;             // K multiple of 64
+  int H, W, Cin;           // im2col geometry (Cin multiple of 64); H == 0 -> plain matrix
+  int relu;
+  int m_tiles, n_blocks, splits, slices_per_split;
+};
+
+__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
+  extern __shared__ uint8_t smem_raw[];
+  ConvTcSmem& s = *reinterpret_cast<ConvTcSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total_jobs = job.m_tiles * job.n_blocks * job.splits;
+  const int my_jobs = ((int)blockIdx.x < total_jobs) ? (total_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nsl = job.slices_per_split;
+
+  if (tid == 0) {
+    for (int i = 0; i < CT_NA; ++i) { tc::mbar_init(&s.afull[i], 4); tc::mbar_init(&s.aempty[i], 1); }
+    for (int i = 0; i < CT_NB; ++i) { tc::mbar_init(&s.bfull[i], 1); tc::mbar_init(&s.bempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.acc_full[i], 1); tc::mbar_init(&s.acc_free[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc_cg1(&s.tmem_base, 256);
+    tc::tmem_relinquish_cg1();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+
+  // job index -> (m-tile, n-block, split): n-block fastest so neighbouring CTAs share the A rows in L2
+  auto decode = [&](int j, int& mt, int& nb, int& sp) {
+    nb = j % job.n_blocks;
+    const int r = j / job.n_blocks;
+    mt = r % job.m_tiles;
+    sp = r / job.m_tiles;
+  };
+
+  if (warp == 0) {
+    // ===================== B producer =====================
+    if (lane == 0) {
+      uint32_t seq = 0;
+      for (int jj = 0; jj < my_jobs; ++jj) {
+        int mt, nb, sp;
+        decode((int)blockIdx.x + jj * (int)gridDim.x, mt, nb, sp);
+        const uint8_t* src = job.wpk + ((size_t)nb * (job.K / 64) + (size_t)sp * nsl) * CT_B_STAGE;
+        for (int t = 0; t < nsl; ++t, ++seq) {
+          const int st = seq % CT_NB;
+          tc::mbar_wait(&s.bempty[st], ((seq / CT_NB) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&s.bfull[st], CT_B_STAGE);
+          tc::bulk_g2s(s.b[st], src + (size_t)t * CT_B_STAGE, CT_B_STAGE, &s.bfull[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+    const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(s.a[0][0]));
+    const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(s.b[0]));
+    uint32_t ast = 0, aph = 0, bst = 0, bph = 0;
+    for (int jj = 0; jj < my_jobs; ++jj) {
+      const int buf = jj & 1;
+      if (jj >= 2) {      // the epilogue must have drained this accumulator (job jj-2)
+        tc::mbar_wait(&s.acc_free[buf], ((jj >> 1) - 1) & 1);
+        tc::tc_fence_after_sync();
+      }
+      const uint32_t d = tmem + (uint32_t)buf * 128u;
+      for (int t = 0; t < nsl; ++t) {
+        tc::mbar_wait(&s.afull[ast], aph);
+        tc::mbar_wait(&s.bfull[bst], bph);
+        tc::tc_fence_after_sync();
+        const uint32_t a_hi = a_lo0 + ast * ((2 * CT_A_HALF) >> 4), a_lo = a_hi + (CT_A_HALF >> 4);
+        const uint32_t b_hi = b_lo0 + bst * (CT_B_STAGE >> 4), b_lo = b_hi + (CT_B_TILE >> 4);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc::mma_cg1_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc::mma_cg1_lo(d, a_lo + 2u * k, b_hi + 2u * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc::mma_cg1_lo(d, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
+          tc::commit_cg1(&s.aempty[ast]);
+          tc::commit_cg1(&s.bempty[bst]);
+        }
+        __syncwarp();
+        if (++ast == CT_NA) { ast = 0; aph ^= 1u; }
+        if (++bst == CT_NB) { bst = 0; bph ^= 1u; }
+      }
+      if (tc::elect_one()) tc::commit_cg1(&s.acc_full[buf]);
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    for (int jj = 0; jj < my_jobs; ++jj) {
+      int mt, nb, sp;
+      decode((int)blockIdx.x + jj * (int)gridDim.x, mt, nb, sp);
+      const int buf = jj & 1;
+      tc::mbar_wait(&s.acc_full[buf], (jj >> 1) & 1);
+      tc::tc_fence_after_sync();
+      const int m = mt * 128 + row;
+      const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * 128u;
+      float* dst = job.ws ? job.ws + ((size_t)sp * job.M + m) * job.N + (size_t)nb * 128
+                          : job.C + (size_t)m * job.N + (size_t)nb * 128;
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld_x32(taddr + c0, r);
+        tc::tmem_ld_wait();
+        if (m < job.M && nb * 128 + c0 < job.N) {     // N is a multiple of 32; the padded columns are never stored
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v = __uint_as_float(r[j + q]);
+              if (!job.ws) {
+                if (job.bias) v += __ldg(job.bias + nb * 128 + c0 + j + q);
+                if (job.relu) v = fmaxf(v, 0.f);
+              }
+              op[q] = v;
+            }
+            *reinterpret_cast<float4*>(dst + c0 + j) = o;
+          }
+        }
+      }
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.acc_free[buf]);
+    }
+  } else if (warp >= 8) {
+    // ===================== A producers: two groups of 4 warps, alternating slices =====================
+    const int grp = (warp - 8) >> 2;                 // 0 / 1
+    const int row = ((warp - 8) & 3) * 32 + lane;    // pixel row of the tile
+    uint32_t seq = 0;                                // global slice counter (all jobs)
+    for (int jj = 0; jj < my_jobs; ++jj) {
+      int mt, nb, sp;
+      decode((int)blockIdx.x + jj * (int)gridDim.x, mt, nb, sp);
+      const int m = mt * 128 + row;
+      int py = 0, px = 0;
+      const float* img = job.A;
+      if (job.H > 0) {
+        const int hw = job.H * job.W;
+        const int b = m / hw, r = m % hw;
+        py = r / job.W; px = r % job.W;
+        img = job.A + (size_t)b * hw * job.Cin;
+      }
+      for (int t = 0; t < nsl; ++t, ++seq) {
+        if ((int)(seq & 1u) != grp) continue;
+        const uint32_t use = seq >> 1;                           // this group's slice counter
+        const int slot = grp * 2 + (int)(use & 1u);
+        const int k0 = (sp * nsl + t) * 64;
+        const float* src = nullptr;
+        if (m < job.M) {
+          if (job.H > 0) {
+            const int tap = k0 / job.Cin, ci = k0 % job.Cin;
+            const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+            if (yy >= 0 && yy < job.H && xx >= 0 && xx < job.W) src = img + ((size_t)yy * job.W + xx) * job.Cin + ci;
+          } else {
+            src = job.A + (size_t)m * job.K + k0;
+          }
+        }
+        float4 v[16];
+        if (src) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tc::mbar_wait(&s.aempty[slot], ((use >> 1) & 1) ^ 1);
+        uint8_t* ahi = s.a[slot][0];
+        uint8_t* alo = s.a[slot][1];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                            // 8 chunks of 8 bf16 (16 B)
+          uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+          tc::split_bf16x2(v[2 * c].x, v[2 * c].y, h0, l0);
+          tc::split_bf16x2(v[2 * c].z, v[2 * c].w, h1, l1);
+          tc::split_bf16x2(v[2 * c + 1].x, v[2 * c + 1].y, h2, l2);
+          tc::split_bf16x2(v[2 * c + 1].z, v[2 * c + 1].w, h3, l3);
+          const uint32_t off = tc::sw128_offset((uint32_t)row, (uint32_t)c);
+          *reinterpret_cast<uint4*>(ahi + off) = make_uint4(h0, h1, h2, h3);
+          *reinterpret_cast<uint4*>(alo + off) = make_uint4(l0, l1, l2, l3);
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s.afull[slot]);
+      }
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc_cg1(tmem, 256);
+}
+
+}  // namespace
+
+// [K, N] fp32 row-major (device) -> packed B stage images [N/128][K/64][hi|lo][128 x 64 SW128 bf16] (device)
+int conv_tc_pack(const float* d_w, int K, int N, uint8_t** out_dev) {
+  std::vector<float> w((size_t)K * N);
+  DISN_CUDA_OK(cudaMemcpy(w.data(), d_w, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  const int ns = K / 64, nbk = (N + 127) / 128;
+  std::vector<uint8_t> img((size_t)nbk * ns * CT_B_STAGE, 0);   // rows beyond N stay zero
+  for (int nb = 0; nb < nbk; ++nb)
+    for (int t = 0; t < ns; ++t)
+      for (int part = 0; part < 2; ++part) {
+        uint8_t* dst = img.data() + ((size_t)nb * ns + t) * CT_B_STAGE + (size_t)part * CT_B_TILE;
+        for (int nl = 0; nl < 128 && nb * 128 + nl < N; ++nl)
+          for (int k = 0; k < 64; ++k) {
+            const float v = w[(size_t)(t * 64 + k) * N + nb * 128 + nl];
+            const __nv_bfloat16 hi = __float2bfloat16(v);
+            const __nv_bfloat16 o = part == 0 ? hi : __float2bfloat16(v - __bfloat162float(hi));
+            memcpy(dst + tc::sw128_offset(nl, k / 8) + (k % 8) * 2, &o, 2);
+          }
+      }
+  DISN_CUDA_OK(cudaMalloc(out_dev, img.size()));
+  DISN_CUDA_OK(cudaMemcpy(*out_dev, img.data(), img.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// returns the number of K splits used (>= 1); when > 1 the caller reduces `ws` (splits x M x N) afterwards
+int launch_conv_tc(disn_ctx* c, const float* A, const uint8_t* wpk, const float* bias, float* C, float* ws,
+                   int64_t ws_elems, int M, int N, int K, int H, int W, int Cin, int relu, int* splits_out) {
+  DISN_REQUIRE(K % 64 == 0 && N % 32 == 0 && (H == 0 || Cin % 64 == 0), "conv_tc: K%64, N%32, Cin%64");
+  static bool attr_set = false;
+  const int smem = (int)sizeof(ConvTcSmem) + 1024;
+  if (!attr_set) {
+    DISN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
+  ConvTcJob job{};
+  job.A = A; job.wpk = wpk; job.bias = bias; job.C = C; job.M = M; job.N = N; job.K = K;
+  job.H = H; job.W = W; job.Cin = Cin; job.relu = relu;
+  job.m_tiles = (M + 127) / 128;
+  job.n_blocks = (N + 127) / 128;
+  const int slices = K / 64;
+  int splits = 1;
+  const int tiles = job.m_tiles * job.n_blocks;
+  if (tiles < sms) {                     // under-filled: split K so that ~2 waves of jobs exist
+    int want = (2 * sms + tiles - 1) / tiles;
+    for (int d = std::min(want, slices); d >= 1; --d)
+      if (slices % d == 0 && (int64_t)d * M * N <= ws_elems) { splits = d; break; }
+  }
+  job.splits = splits;
+  job.slices_per_split = slices / splits;
+  job.ws = splits > 1 ? ws : nullptr;
+  const int total = tiles * splits;
+  conv_tc_kernel<<<std::min(total, sms), CT_THREADS, smem, c->stream>>>(job);
+  c->launches++;
+  DISN_CUDA_OK(cudaGetLastError());
+  *splits_out = splits;
+  return 0;
+}
+
+}  // namespace disn

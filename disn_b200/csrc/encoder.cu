@@ -248,6 +248,30 @@ static int launch_gemm(disn_ctx* c, int mode, const float* A, const float* Bm, c
   return 0;
 }
 
+// GEMM dispatcher: tcgen05 path (bf16 hi/lo split, fp32 accumulate) when the context runs in DISN_PREC_BF16X3 and
+// the shapes fit (K % 64 == 0, channels % 64 == 0); fp32 CUDA-core path otherwise (conv1_1: Cin = 3).
+static int gemm_any(disn_ctx* c, const std::string& wname, int mode, const float* A, const float* Bm, const float* bias,
+                    float* C, int M, int N, int K, int relu, ConvGeom g) {
+  const bool tc_ok = c->cfg.precision == DISN_PREC_BF16X3 && K % 64 == 0 && N % 32 == 0 &&
+                     (mode == A_PLAIN || g.Cin % 64 == 0);
+  if (!tc_ok) return launch_gemm(c, mode, A, Bm, bias, C, M, N, K, relu, g);
+  uint8_t*& pk = c->enc_tc_weights[wname];
+  if (!pk && conv_tc_pack(Bm, K, N, &pk)) return -1;
+  int splits = 1;
+  if (launch_conv_tc(c, A, pk, bias, C, c->splitk_ws, c->splitk_ws_elems, M, N, K, mode == A_IM2COL ? g.H : 0,
+                     g.W, g.Cin, relu, &splits))
+    return -1;
+  if (splits > 1) {
+    const int64_t mn4 = (int64_t)M * N / 4;
+    int blocks = (int)std::min<int64_t>((mn4 + 255) / 256, 148 * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->splitk_ws), bias,
+                                                       reinterpret_cast<float4*>(C), mn4, N / 4, splits, relu);
+    c->launches++;
+    DISN_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // 2x2 / stride-2 VALID max pool, NHWC, C % 4 == 0
 // ------------------------------------------------------------------------------------------------
@@ -461,8 +485,8 @@ int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool
     bool is_tap = (tap < 5 && kTapLayer[tap] == i);
     float* y = is_tap ? c->taps[tap] : c->act[pp];
     ConvGeom g{hw, hw, kConvCin[i]};
-    if (launch_gemm(c, A_IM2COL, x, wptr(c, std::string(kConvName[i]) + "/weights"),
-                    wptr(c, std::string(kConvName[i]) + "/biases"), y, B * hw * hw, kConvCout[i], 9 * kConvCin[i], 1, g))
+    if (gemm_any(c, std::string(kConvName[i]) + "/weights", A_IM2COL, x, wptr(c, std::string(kConvName[i]) + "/weights"),
+                 wptr(c, std::string(kConvName[i]) + "/biases"), y, B * hw * hw, kConvCout[i], 9 * kConvCin[i], 1, g))
       return -1;
     x = y;
     if (!is_tap) pp ^= 1;
@@ -497,8 +521,8 @@ int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool
   for (int l = 0; l < 5; ++l) {
     int hw = kTapHW[l];
     ConvGeom g{0, 0, 0};
-    if (launch_gemm(c, A_PLAIN, c->taps[l], wl + (int64_t)off * kHidden, nullptr, c->proj[l], B * hw * hw, kHidden,
-                    kTapC[l], 0, g))
+    if (gemm_any(c, "proj" + std::to_string(l), A_PLAIN, c->taps[l], wl + (int64_t)off * kHidden, nullptr, c->proj[l],
+                 B * hw * hw, kHidden, kTapC[l], 0, g))
       return -1;
     off += kTapC[l];
     lv.p[l] = c->proj[l];

@@ -131,3 +131,24 @@ def test_batch_of_eight_images(he_weights):
             assert np.abs(grid[b].reshape(-1) - ref.reshape(-1)).max() <= 1e-4
     finally:
         eng.close()
+
+
+def test_tc_encoder_matches_oracle(tc_engine, he_weights):
+    """Encoder GEMMs on tcgen05 (bf16 hi/lo split): taps, embedding and folded products vs the fp64 oracle."""
+    from disn_b200 import synth
+    from oracle import disn_oracle as orc
+    imgs = synth.synthetic_images(2, seed=4321)
+    tc_engine.encode(imgs)
+    enc = orc.encode(imgs, he_weights, dtype=np.float64)
+    for i, tap in enumerate(orc.VGG_TAPS):
+        got, ref = tc_engine.get_encoded(1 + i), enc.vgg_end_points[tap]
+        assert np.abs(got - ref).max() <= 5e-5 * np.abs(ref).max(), tap
+    emb = tc_engine.get_encoded(0)
+    assert np.abs(emb - enc.img_embedding).max() <= 5e-5 * np.abs(enc.img_embedding).max()
+    Wl = he_weights["sdfprediction_imgfeat/fold2/conv1/weights"].reshape(-1, 512).astype(np.float64)
+    off, pmap = 512, 0
+    for m, c in zip(enc.maps, orc.TAP_CHANNELS):
+        pmap = pmap + m @ Wl[off:off + c]
+        off += c
+    got = tc_engine.get_encoded(6)
+    assert np.abs(got - pmap).max() <= 5e-5 * np.abs(pmap).max()
