@@ -197,9 +197,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
         img = job.A + (size_t)b * hw * job.Cin;
       }
       for (int t = 0; t < nsl; ++t, ++seq) {
-        if ((int)(seq & 1u) != grp) continue;
-        const uint32_t use = seq >> 1;                           // this group's slice counter
-        const int slot = grp * 2 + (int)(use & 1u);
+        if ((int)(seq & 1u) != grp) continue;                  // odd / even slices belong to the two groups
+        const int slot = (int)(seq & 3u);                        // the consumer walks the ring in slice order
+        const uint32_t use = seq >> 2;                           // uses of this slot so far
         const int k0 = (sp * nsl + t) * 64;
         const float* src = nullptr;
         if (m < job.M) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        tc::mbar_wait(&s.aempty[slot], ((use >> 1) & 1) ^ 1);
+        tc::mbar_wait(&s.aempty[slot], (use & 1) ^ 1);
         uint8_t* ahi = s.a[slot][0];
         uint8_t* alo = s.a[slot][1];
 #pragma unroll
