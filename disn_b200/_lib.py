@@ -47,6 +47,8 @@ EXPORTS = {
                                       C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int64),
                                       C.c_uint32]),
     "disn_launch_count": (C.c_int64, [C.c_void_p]),
+    "disn_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "disn_tc_stream_probe": (C.c_int, [C.c_int]),
     "disn_tc_selftest": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 }

@@ -116,7 +116,8 @@ int disn_load_weight(disn_ctx* c, const char* name, const float* data, const int
   }
   t.shape = shp;
   t.numel = numel;
-  DISN_CUDA_OK(cudaMemcpy(t.ptr, data, numel * sizeof(float), cudaMemcpyHostToDevice));
+  DISN_CUDA_OK(cudaMemcpyAsync(t.ptr, data, numel * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));   // caller-owned host buffer; ordered on the ctx stream
   c->weights_dirty = true;
   for (auto& kv : c->enc_tc_weights) cudaFree(kv.second);     // packed encoder weights follow the fp32 masters
   c->enc_tc_weights.clear();

@@ -128,7 +128,7 @@ int launch_point_fp32(disn_ctx* c, const PointJob& job);
 int tc_pack_weights(disn_ctx* c);
 int launch_point_tc(disn_ctx* c, const PointJob& job);
 // conv_tc.cu
-int conv_tc_pack(const float* d_w, int K, int N, uint8_t** out_dev);
+int conv_tc_pack(disn_ctx* c, const float* d_w, int K, int N, uint8_t** out_dev);
 int launch_conv_tc(disn_ctx* c, const float* A, const uint8_t* wpk, const float* bias, float* C, float* ws,
                    int64_t ws_elems, int M, int N, int K, int H, int W, int Cin, int relu, int* splits_out);
 // chamfer.cu

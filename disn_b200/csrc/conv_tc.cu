@@ -247,9 +247,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
 }  // namespace
 
 // [K, N] fp32 row-major (device) -> packed B stage images [N/128][K/64][hi|lo][128 x 64 SW128 bf16] (device)
-int conv_tc_pack(const float* d_w, int K, int N, uint8_t** out_dev) {
+int conv_tc_pack(disn_ctx* c, const float* d_w, int K, int N, uint8_t** out_dev) {
   std::vector<float> w((size_t)K * N);
-  DISN_CUDA_OK(cudaMemcpy(w.data(), d_w, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  DISN_CUDA_OK(cudaMemcpyAsync(w.data(), d_w, w.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
   const int ns = K / 64, nbk = (N + 127) / 128;
   std::vector<uint8_t> img((size_t)nbk * ns * CT_B_STAGE, 0);   // rows beyond N stay zero
   for (int nb = 0; nb < nbk; ++nb)
@@ -264,8 +265,11 @@ int conv_tc_pack(const float* d_w, int K, int N, uint8_t** out_dev) {
             memcpy(dst + tc::sw128_offset(nl, k / 8) + (k % 8) * 2, &o, 2);
           }
       }
+  // copy on the context's (non-blocking) stream and wait: a plain cudaMemcpy from pageable memory may return before
+  // the DMA has landed and is not ordered against kernels on a non-blocking stream
   DISN_CUDA_OK(cudaMalloc(out_dev, img.size()));
-  DISN_CUDA_OK(cudaMemcpy(*out_dev, img.data(), img.size(), cudaMemcpyHostToDevice));
+  DISN_CUDA_OK(cudaMemcpyAsync(*out_dev, img.data(), img.size(), cudaMemcpyHostToDevice, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -256,7 +256,7 @@ static int gemm_any(disn_ctx* c, const std::string& wname, int mode, const float
                      (mode == A_PLAIN || g.Cin % 64 == 0);
   if (!tc_ok) return launch_gemm(c, mode, A, Bm, bias, C, M, N, K, relu, g);
   uint8_t*& pk = c->enc_tc_weights[wname];
-  if (!pk && conv_tc_pack(Bm, K, N, &pk)) return -1;
+  if (!pk && conv_tc_pack(c, Bm, K, N, &pk)) return -1;
   int splits = 1;
   if (launch_conv_tc(c, A, pk, bias, C, c->splitk_ws, c->splitk_ws_elems, M, N, K, mode == A_IM2COL ? g.H : 0,
                      g.W, g.Cin, relu, &splits))
@@ -445,6 +445,45 @@ int encoder_alloc(disn_ctx* c, int B) {
   c->alloc_B = B;
   return 0;
 }
+
+}  // namespace disn
+// Diagnostic: run one GEMM (plain if H == 0, else 3x3 SAME im2col of an NHWC tensor) through both the fp32
+// CUDA-core kernel and the tcgen05 kernel; host pointers.  Used by the GPU test-suite to sweep shapes.
+extern "C" int disn_debug_gemm(disn_ctx* c, const float* A, const float* Wt, const float* bias, int M, int N, int K,
+                               int H, int Wd, int Cin, int relu, float* out_fp32, float* out_tc) {
+  using namespace disn;
+  DISN_REQUIRE(c && A && Wt && out_fp32 && out_tc, "null argument");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  if (encoder_alloc(c, 1)) return -1;
+  const size_t a_elems = H ? (size_t)M * Cin : (size_t)M * K;
+  float *dA = nullptr, *dW = nullptr, *dB = nullptr, *dC = nullptr;
+  DISN_CUDA_OK(cudaMalloc(&dA, a_elems * 4)); DISN_CUDA_OK(cudaMalloc(&dW, (size_t)K * N * 4));
+  DISN_CUDA_OK(cudaMalloc(&dC, (size_t)M * N * 4));
+  DISN_CUDA_OK(cudaMemcpy(dA, A, a_elems * 4, cudaMemcpyHostToDevice));
+  DISN_CUDA_OK(cudaMemcpy(dW, Wt, (size_t)K * N * 4, cudaMemcpyHostToDevice));
+  if (bias) { DISN_CUDA_OK(cudaMalloc(&dB, (size_t)N * 4)); DISN_CUDA_OK(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice)); }
+  DISN_CUDA_OK(cudaDeviceSynchronize());   // pageable H2D copies above are not ordered against the ctx stream
+  ConvGeom g{H, Wd, Cin};
+  const int mode = H ? A_IM2COL : A_PLAIN;
+  const int saved = c->cfg.precision;
+  int rc = 0;
+  for (int pass = 0; pass < 2 && rc == 0; ++pass) {
+    c->cfg.precision = pass ? DISN_PREC_BF16X3 : DISN_PREC_FP32;
+    c->enc_tc_weights.erase("debug_gemm");
+    DISN_CUDA_OK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
+    rc = gemm_any(c, "debug_gemm", mode, dA, dW, dB, dC, M, N, K, relu, g);
+    if (rc == 0) {
+      DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+      DISN_CUDA_OK(cudaMemcpy(pass ? out_tc : out_fp32, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  c->cfg.precision = saved;
+  auto it = c->enc_tc_weights.find("debug_gemm");
+  if (it != c->enc_tc_weights.end()) { cudaFree(it->second); c->enc_tc_weights.erase(it); }
+  cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dC);
+  return rc;
+}
+namespace disn {
 
 static const float* wptr(disn_ctx* c, const std::string& name) {
   auto it = c->weights.find(name);

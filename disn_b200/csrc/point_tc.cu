@@ -531,7 +531,8 @@ int tc_pack_weights(disn_ctx* c) {
       DISN_REQUIRE(it != c->weights.end(), "missing variable " + p + names[layer]);
       const int K = Ks[layer], N = Ns[layer];
       std::vector<float> w((size_t)K * N);   // rows 0..K-1 of the [Cin,Cout] matrix (point-feature part)
-      DISN_CUDA_OK(cudaMemcpy(w.data(), it->second.ptr, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      DISN_CUDA_OK(cudaMemcpyAsync(w.data(), it->second.ptr, w.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
       for (int t = 0; t < K / 64; ++t)
         for (int nb = 0; nb < N / 256; ++nb, ++stage)
           for (int part = 0; part < 2; ++part)
@@ -556,7 +557,8 @@ int tc_pack_weights(disn_ctx* c) {
     DISN_CUDA_OK(cudaMalloc(&c->tc_weights, total));
     c->tc_weights_bytes = (int64_t)total;
   }
-  DISN_CUDA_OK(cudaMemcpy(c->tc_weights, img.data(), total, cudaMemcpyHostToDevice));
+  DISN_CUDA_OK(cudaMemcpyAsync(c->tc_weights, img.data(), total, cudaMemcpyHostToDevice, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));   // ordered on the ctx stream (see conv_tc_pack)
   return 0;
 }
 

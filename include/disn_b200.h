@@ -125,6 +125,11 @@ int disn_nn_distance(disn_ctx* ctx, const float* xyz1, const float* xyz2, int32_
  * accumulated; returns the raw TMEM image D_out[2 CTAs][128 lanes][128 columns]. Host pointers. */
 int disn_tc_selftest(int device, const float* A, const float* B, int passes, float* D_out);
 
+/* Diagnostic: one encoder GEMM (plain when H == 0, else the 3x3 SAME im2col view of NHWC A[M/(H*W),H,W,Cin]) through
+ * the fp32 CUDA-core kernel and through the tcgen05 kernel; host pointers, outputs [M,N]. */
+int disn_debug_gemm(disn_ctx* ctx, const float* A, const float* Wt, const float* bias, int M, int N, int K, int H, int W,
+                    int Cin, int relu, float* out_fp32, float* out_tc);
+
 /* Diagnostic: prints the achievable L2 -> shared-memory bulk-copy streaming rate (bytes/clk/SM) for a sweep of
  * ring depths, stage sizes and cluster multicast widths (the weight-streaming pattern of the tensor-core kernel). */
 int disn_tc_stream_probe(int device);
