@@ -116,3 +116,26 @@ def test_two_rank_slab_gather_gloo(R, tmp_path):
     full = np.load(tmp_path / "full.npy")
     np.testing.assert_array_equal(full.reshape(-1), np.arange(R ** 3, dtype=np.float32))
     assert np.load(tmp_path / "tmax.npy")[0] == 2.0
+
+
+def test_tf_checkpoint_bundle_round_trip(tmp_path):
+    """tensor-bundle writer -> reader round trip with the path's variable names/shapes (format restated from
+    TensorFlow's tensor_bundle; unpinned against a real checkpoint, see disn_b200/tf_checkpoint.py)."""
+    from disn_b200 import synth
+    from disn_b200 import tf_checkpoint as ck
+    rng = np.random.default_rng(0)
+    shapes = {k: v for k, v in synth.weight_shapes().items() if "fc6" not in k and "fc7" not in k}
+    tensors = {k: rng.standard_normal(v).astype(np.float32) for k, v in list(shapes.items())[:40]}
+    tensors["global_step"] = np.array(12345, dtype=np.int64)
+    prefix = str(tmp_path / "ckpt" / "model.ckpt")
+    ck.save_checkpoint(prefix, tensors)
+    idx = ck.read_index(prefix + ".index")
+    assert set(idx) == set(tensors)
+    assert idx["vgg_16/conv1/conv1_1/weights"]["shape"] == (3, 3, 3, 64)
+    got = ck.load_checkpoint(prefix, prefixes=("vgg_16/", "sdfprediction"))
+    assert "global_step" not in got and len(got) == len(tensors) - 1
+    for k, v in got.items():
+        np.testing.assert_array_equal(v, tensors[k])
+    with pytest.raises(ValueError, match="bad table magic"):
+        open(prefix + ".bad.index", "wb").write(b"x" * 100)
+        ck.read_index(prefix + ".bad.index")
