@@ -333,6 +333,28 @@ int disn_write_dist(const char* path, int32_t res, const double* bbox, const flo
   return 0;
 }
 
+int disn_cam_estimate(disn_ctx* c, const float* imgs, int32_t B, int32_t H, int32_t W, int32_t C, const float* K,
+                      float* out_rt, float* out_trans_mat) {
+  DISN_REQUIRE(c && imgs && out_trans_mat, "null argument");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  DISN_REQUIRE(B >= 1 && B <= c->cfg.max_batch, "batch exceeds max_batch of the context");
+  if (encoder_run(c, imgs, B, H, W, C, false, /*embedding_only=*/true)) return -1;
+  static const float kDefaultK[9] = {149.84375f, 0.f, 68.5f, 0.f, 149.84375f, 68.5f, 0.f, 0.f, 1.f};
+  float *dK = nullptr, *dRT = nullptr, *dTM = nullptr;
+  auto cleanup = [&]() { cudaFree(dK); cudaFree(dRT); cudaFree(dTM); };
+  cudaError_t e;
+#define CAM_OK(expr) if ((e = (expr)) != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e)); cleanup(); return -1; }
+  CAM_OK(cudaMalloc(&dK, 9 * 4)); CAM_OK(cudaMalloc(&dRT, (size_t)B * 12 * 4)); CAM_OK(cudaMalloc(&dTM, (size_t)B * 12 * 4));
+  CAM_OK(cudaMemcpyAsync(dK, K ? K : kDefaultK, 9 * 4, cudaMemcpyHostToDevice, c->stream));
+  if (launch_cam_heads(c, B, dK, dRT, dTM)) { cleanup(); return -1; }
+  if (out_rt) CAM_OK(cudaMemcpyAsync(out_rt, dRT, (size_t)B * 12 * 4, cudaMemcpyDeviceToHost, c->stream));
+  CAM_OK(cudaMemcpyAsync(out_trans_mat, dTM, (size_t)B * 12 * 4, cudaMemcpyDeviceToHost, c->stream));
+  CAM_OK(cudaStreamSynchronize(c->stream));
+#undef CAM_OK
+  cleanup();
+  return 0;
+}
+
 int disn_nn_distance(disn_ctx* c, const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, float* dist1,
                      int32_t* idx1, float* dist2, int32_t* idx2) {
   DISN_REQUIRE(c && xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "null argument");

@@ -120,7 +120,8 @@ struct disn_ctx {
 namespace disn {
 // encoder.cu
 int encoder_alloc(disn_ctx* c, int B);
-int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool device_ptr);
+int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool device_ptr,
+                bool embedding_only = false);
 void encoder_free(disn_ctx* c);
 // point_fp32.cu
 int launch_point_fp32(disn_ctx* c, const PointJob& job);
@@ -131,6 +132,8 @@ int launch_point_tc(disn_ctx* c, const PointJob& job);
 int conv_tc_pack(disn_ctx* c, const float* d_w, int K, int N, uint8_t** out_dev);
 int launch_conv_tc(disn_ctx* c, const float* A, const uint8_t* wpk, const float* bias, float* C, float* ws,
                    int64_t ws_elems, int M, int N, int K, int H, int W, int Cin, int relu, int* splits_out);
+// cam.cu
+int launch_cam_heads(disn_ctx* c, int B, const float* d_K, float* d_rt, float* d_tm);
 // chamfer.cu
 int nn_distance(disn_ctx* c, const float* d_xyz1, int n, const float* d_xyz2, int m, int B, float* d_dist1,
                 int* d_idx1, float* d_dist2, int* d_idx2);

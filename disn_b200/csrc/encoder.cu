@@ -490,7 +490,7 @@ static const float* wptr(disn_ctx* c, const std::string& name) {
   return it == c->weights.end() ? nullptr : it->second.ptr;
 }
 
-int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool device_ptr) {
+int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool device_ptr, bool embedding_only) {
   DISN_REQUIRE(C == 3, "imgs must have 3 channels (FLAGS.alpha is not on the hot path)");
   DISN_REQUIRE(B >= 1 && B <= GEMV_MAXB, "batch must be in [1,8]");
   const int V = c->cfg.vgg_in;
@@ -501,9 +501,11 @@ int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool
                  std::string("missing weights for ") + kConvName[i]);
   }
   for (const char* nm : {"vgg_16/fc6", "vgg_16/fc7", "vgg_16/fc8", "sdfprediction/fold2/conv1",
-                         "sdfprediction_imgfeat/fold2/conv1"})
+                         "sdfprediction_imgfeat/fold2/conv1"}) {
+    if (embedding_only && std::string(nm).rfind("sdfprediction", 0) == 0) continue;
     DISN_REQUIRE(wptr(c, std::string(nm) + "/weights") && wptr(c, std::string(nm) + "/biases"),
                  std::string("missing weights for ") + nm);
+  }
 
   DISN_CUDA_OK(cudaMemcpyAsync(c->img_in, imgs, (size_t)B * H * W * C * sizeof(float),
                                device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
@@ -549,6 +551,10 @@ int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool
   if (launch_gemv(c, c->fc_b, wptr(c, "vgg_16/fc8/weights"), wptr(c, "vgg_16/fc8/biases"), c->emb, B, 4096,
                   c->cfg.num_classes, 0))
     return -1;
+  if (embedding_only) {      // camera-pose net: only the VGG embedding is needed
+    c->enc_B = 0;
+    return 0;
+  }
   // global-feature fold: gbias = emb * Wg[512:512+nc, :] + b   (models/sdfnet.py:78-85)
   if (launch_gemv(c, c->emb, wptr(c, "sdfprediction/fold2/conv1/weights") + (int64_t)kHidden * kHidden,
                   wptr(c, "sdfprediction/fold2/conv1/biases"), c->gbias, B, c->cfg.num_classes, kHidden, 0))

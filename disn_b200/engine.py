@@ -144,6 +144,28 @@ class Engine:
         check(self.lib.disn_eval_grid(self._h, sp.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(trans_mat_ptr),
                                       sp.shape[0], sdf_res, z0, z1, C.c_void_p(out_ptr), DISN_DEVICE_PTR))
 
+    # -- estimated camera ------------------------------------------------------------------------
+    def cam_estimate(self, imgs, K=None, want_rt: bool = False):
+        """demo/demo.py:195-258 cam_evl: imgs [B,H,W,3] -> pred_trans_mat [B,4,3] (this engine must hold the camera
+        checkpoint's variables: vgg_16/* and cameraprediction/*).  load_weights_raw() skips the SDF-head checks."""
+        a = _f32(imgs)
+        B, H, W, Cc = a.shape
+        tm = np.empty((B, 4, 3), np.float32)
+        rt = np.empty((B, 4, 3), np.float32) if want_rt else None
+        kk = None if K is None else _f32(K).reshape(9)
+        check(self.lib.disn_cam_estimate(self._h, a.ctypes.data_as(C.c_void_p), B, H, W, Cc,
+                                         None if kk is None else kk.ctypes.data_as(C.c_void_p),
+                                         None if rt is None else rt.ctypes.data_as(C.c_void_p),
+                                         tm.ctypes.data_as(C.c_void_p)))
+        return (tm, rt) if want_rt else tm
+
+    def load_weights_raw(self, weights: dict):
+        """Upload variables without finalising the SDF heads (camera-net contexts have no sdfprediction/*)."""
+        for name, arr in weights.items():
+            a = _f32(arr)
+            shp = (C.c_int64 * a.ndim)(*a.shape)
+            check(self.lib.disn_load_weight(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), shp, a.ndim))
+
     # -- mesh metrics -------------------------------------------------------------------------
     def nn_distance(self, xyz1, xyz2):
         """The reference's tf_nndistance.nn_distance(xyz1, xyz2): squared NN distances + indices, both ways."""

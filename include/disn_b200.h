@@ -114,6 +114,14 @@ int disn_write_obj(const char* path, const float* verts, int64_t n_verts, const 
 int disn_marching_cubes(disn_ctx* ctx, const float* sdf, int32_t R, const double* bbox, float iso,
                         float* verts, int64_t* n_verts, int32_t* faces, int64_t* n_faces, uint32_t flags);
 
+/* Estimated-camera path (reference: demo/demo.py:195-258 cam_evl, cam_est/model_cam.py:47-109, models/posenet.py:91-124):
+ * imgs host [B,H,W,3] -> VGG-16 embedding (the context's `vgg_16/...` weights = the camera checkpoint's) -> three FC
+ * heads (`cameraprediction/{scale,ortho6d,translation}/fc{1,2,3}/{weights,biases}`) -> pred_RT [B,4,3] (or NULL) and
+ * pred_trans_mat = pred_RT . K^T [B,4,3].  K: host float[9] row-major intrinsics, NULL = the reference constant
+ * [[149.84375,0,68.5],[0,149.84375,68.5],[0,0,1]] (cam_est/model_cam.py:28). */
+int disn_cam_estimate(disn_ctx* ctx, const float* imgs, int32_t B, int32_t H, int32_t W, int32_t C, const float* K,
+                      float* out_rt, float* out_trans_mat);
+
 /* Chamfer nearest-neighbour distances, the reference's NnDistance op (models/tf_ops/nn_distance/tf_nndistance.cpp:
  * 21-43; called at test/test_cd_emd.py:300, test/test_f_score.py:253): xyz1 [B,N,3], xyz2 [B,M,3] host float32 ->
  * dist1 [B,N] (squared L2 to the nearest point of xyz2), idx1 [B,N] int32, dist2 [B,M], idx2 [B,M].

@@ -363,3 +363,54 @@ def folded_decode(enc, sample_pc, trans_mat, W, dtype=np.float64):
     pg = stream("sdfprediction", gbias.reshape(B, 1, 512))
     pl = stream("sdfprediction_imgfeat", pfeat + np.asarray(W["sdfprediction_imgfeat/fold2/conv1/biases"], dtype))
     return pg + pl
+
+
+# ----------------------------------------------------------------------------------------
+# estimated-camera path (cam_est/model_cam.py:47-109, models/posenet.py:22-36,91-124)
+# ----------------------------------------------------------------------------------------
+CAM_K = np.array([[149.84375, 0., 68.5], [0., 149.84375, 68.5], [0., 0., 1.]], dtype=np.float64)   # model_cam.py:28
+CAM_T_OFFSET = np.array([-0.00193892, 0.00169222, 1.3949631])                                        # posenet.py:118
+
+
+def cam_head_shapes():
+    s = {}
+    for head, dims in (("scale", (1024, 64, 32, 1)), ("ortho6d", (1024, 512, 256, 6)), ("translation", (1024, 128, 64, 3))):
+        for i in range(3):
+            s["cameraprediction/%s/fc%d/weights" % (head, i + 1)] = (dims[i], dims[i + 1])
+            s["cameraprediction/%s/fc%d/biases" % (head, i + 1)] = (dims[i + 1],)
+    return s
+
+
+def rotation_from_ortho6d(poses):
+    """models/posenet.py:22-36."""
+    x_raw, y_raw = poses[:, 0:3], poses[:, 3:6]
+    nrm = lambda v: v / np.maximum(np.sqrt((v * v).sum(1, keepdims=True)), 1e-8)
+    x = nrm(x_raw)
+    z = nrm(np.cross(x, y_raw))
+    y = np.cross(z, x)
+    return np.stack([x, y, z], axis=2)
+
+
+def cam_estimate(imgs, W, K=CAM_K, dtype=np.float64):
+    """model_cam.get_model (non-shift branch): -> (pred_RT [B,4,3], pred_trans_mat [B,4,3])."""
+    img = np.asarray(imgs, dtype)
+    if img.shape[1] != VGG_IN or img.shape[2] != VGG_IN:
+        img = tf_resize_bilinear(img, VGG_IN, VGG_IN, dtype)
+    net, _ = vgg_16(img, {k: np.asarray(v, dtype) for k, v in W.items() if k.startswith("vgg_16")}, dtype)
+    g = net.reshape(net.shape[0], -1)
+
+    def head(name):
+        h = g
+        for i in (1, 2, 3):
+            h = h @ np.asarray(W["cameraprediction/%s/fc%d/weights" % (name, i)], dtype) + \
+                np.asarray(W["cameraprediction/%s/fc%d/biases" % (name, i)], dtype)
+            if i < 3:
+                h = np.maximum(h, 0)
+        return h
+
+    scale = head("scale").reshape(-1, 1, 1) * np.eye(3)[None]
+    R = rotation_from_ortho6d(head("ortho6d"))
+    t = head("translation") + CAM_T_OFFSET
+    Rs = scale @ R
+    RT = np.concatenate([Rs, t[:, None, :]], axis=1)
+    return RT, RT @ np.asarray(K, dtype).T

@@ -135,3 +135,28 @@ def test_errors_are_loud(engine):
     with pytest.raises(DisnError):
         engine.eval_grid(synth.DEMO_SDF_PARAMS.repeat(engine.batch, 0),
                          synth.DEMO_TRANS_MAT.repeat(engine.batch, 0), 8, z0=5, z1=20)
+
+
+def test_camera_pose_net_matches_oracle(he_weights):
+    """--cam_est path (demo/demo.py:195-258): VGG embedding -> pose heads -> pred_RT . K^T."""
+    from disn_b200.engine import Engine
+    rng = np.random.default_rng(3)
+    W = {k: v for k, v in he_weights.items() if k.startswith("vgg_16/")}
+    for name, shp in orc.cam_head_shapes().items():
+        W[name] = (rng.standard_normal(shp) * (0.02 if name.endswith("biases") else np.sqrt(2.0 / shp[0]))).astype(np.float32)
+    imgs = synth.synthetic_images(2, seed=77)
+    for prec in ("fp32", "bf16x3"):
+        eng = Engine(device=0, precision=prec, max_batch=2)
+        try:
+            eng.load_weights_raw(W)
+            tm, rt = eng.cam_estimate(imgs, want_rt=True)
+        finally:
+            eng.close()
+        ref_rt, ref_tm = orc.cam_estimate(imgs, W)
+        assert tm.shape == (2, 4, 3) and rt.shape == (2, 4, 3)
+        assert np.abs(rt - ref_rt).max() <= 2e-4 * max(1.0, np.abs(ref_rt).max()), prec
+        assert np.abs(tm - ref_tm).max() <= 2e-4 * np.abs(ref_tm).max(), prec
+        # rotation block is a scaled orthonormal frame
+        Rm = rt[:, :3, :]
+        s2 = (Rm[:, :, 0] ** 2).sum(1)
+        np.testing.assert_allclose(np.einsum("bij,bik->bjk", Rm, Rm), s2[:, None, None] * np.eye(3)[None], atol=1e-3 * s2.max())

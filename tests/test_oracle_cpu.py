@@ -120,3 +120,15 @@ def test_nn_distance_oracle_matches_reference_compiled_op():
     brute = ((x1[0][:, None] - x2[0][None]) ** 2).sum(-1)
     np.testing.assert_allclose(d1[0], brute.min(1), rtol=1e-6)
     np.testing.assert_array_equal(i1[0], brute.argmin(1))
+
+
+def test_rotation_from_ortho6d_is_orthonormal_and_right_handed():
+    """models/posenet.py:22-36: columns (x, y, z) orthonormal with z = x × y_raw normalised, det +1."""
+    from oracle import disn_oracle as orc
+    rng = np.random.default_rng(0)
+    R = orc.rotation_from_ortho6d(rng.standard_normal((16, 6)))
+    np.testing.assert_allclose(np.einsum("bij,bik->bjk", R, R), np.broadcast_to(np.eye(3), (16, 3, 3)), atol=1e-12)
+    np.testing.assert_allclose(np.linalg.det(R), 1.0, atol=1e-12)
+    # already-orthonormal input is reproduced
+    eye6 = np.array([[1., 0, 0, 0, 1, 0]])
+    np.testing.assert_allclose(orc.rotation_from_ortho6d(eye6)[0], np.eye(3), atol=0)
