@@ -262,12 +262,15 @@ def run_ours(args):
             t = json.load(open(tpath))
             if t.get("sdf_res") == args.res:
                 traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-        passes = 3 if args.precision == "bf16x3" else 1
+        passes = {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1)     # tensor-pipe time in bf16-rate MMA units per product
+        dtype_s = {"fp32": "f32",
+                   "bf16x3": "bf16x3 (bf16 hi/lo split operands, 3 MMAs/product, fp32 accumulate)",
+                   "f16f8": "f16+e5m2x2 (fp16 product + two e5m2 correction products at 2x rate, fp32 accumulate)"}[args.precision]
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16x3 (bf16 hi/lo split operands, 3 MMAs/product, fp32 accumulate)",
+            "dtype": dtype_s,
             "data": "synthetic",
             "config": {"workload": "single 137x137 image, --sdf_res %d (%d^3 = %d points), twostream, encoder included per step"
                                    % (args.res, R, total_pts),
@@ -278,7 +281,7 @@ def run_ours(args):
                          "kernel_ms": k_ms, "flop_per_point": F_ALG,
                          "algorithmic_bytes": int(slab_pts * 4),
                          "executed_tflops": achieved * passes,
-                         "note": "frac counts the algorithmic FLOPs once; the bf16 hi/lo split executes %dx that on the tensor pipe"
+                         "note": "frac counts the algorithmic FLOPs once; the split-operand scheme spends %dx that in bf16-rate tensor-pipe time"
                                  % passes if passes > 1 else "CUDA-core fp32 path reported against the tensor roofline",
                          "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["source"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(img_host.numel() * 4 + tm_host.numel() * 4),
@@ -302,7 +305,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=256)
-    ap.add_argument("--precision", default=os.environ.get("DISN_PRECISION", "bf16x3"), choices=["fp32", "bf16x3"])
+    ap.add_argument("--precision", default=os.environ.get("DISN_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "f16f8"])
     ap.add_argument("--cpu-sample", type=int, default=8192, dest="cpu_sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

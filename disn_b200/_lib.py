@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libdisn_b200.so")
 DISN_DEVICE_PTR = 1
 PREC_FP32 = 0
 PREC_BF16X3 = 1
+PREC_F16F8 = 2
 
 
 class DisnConfig(C.Structure):
@@ -53,6 +54,8 @@ EXPORTS = {
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "disn_tc_stream_probe": (C.c_int, [C.c_int]),
     "disn_tc_selftest": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "disn_tc_selftest_mixed": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -95,7 +95,8 @@ int disn_synchronize(disn_ctx* c) {
 
 int disn_set_precision(disn_ctx* c, int32_t precision) {
   DISN_REQUIRE(c, "null ctx");
-  DISN_REQUIRE(precision == DISN_PREC_FP32 || precision == DISN_PREC_BF16X3, "unknown precision");
+  DISN_REQUIRE(precision == DISN_PREC_FP32 || precision == DISN_PREC_BF16X3 || precision == DISN_PREC_F16F8,
+               "unknown precision");
   c->cfg.precision = precision;
   return 0;
 }
@@ -217,7 +218,7 @@ static int run_job(disn_ctx* c, PointJob& job) {
   job.tanh_out = c->cfg.tanh_out;
   fill_stream(c, "sdfprediction", job.g);
   fill_stream(c, "sdfprediction_imgfeat", job.l);
-  if (c->cfg.precision == DISN_PREC_BF16X3) return launch_point_tc(c, job);
+  if (c->cfg.precision != DISN_PREC_FP32) return launch_point_tc(c, job);
   return launch_point_fp32(c, job);
 }
 

@@ -73,6 +73,8 @@ struct PointJob {
   float out_scale;        // 1 (eval_points) or 1/sdf_weight (eval_grid)
   int32_t tanh_out;
   StreamWeights g, l;
+  // DISN_PREC_F16F8: power-of-two multipliers of the e5m2 correction operands, [stream][layer]{(a-h(a)) scale, a scale}
+  float act_scale[2][4][2];
   // outputs
   float* out_pred;        // [B,N]
   float* out_uv;          // [B,N,2] or nullptr
@@ -112,8 +114,10 @@ struct disn_ctx {
   int32_t axes_R = 0;
   std::vector<double> axes_key; // (sdf_params, R) the tables in d_axes were built from
   // bf16x3 packed weights (tcgen05 path)
-  void* tc_weights = nullptr;
+  void* tc_weights = nullptr;          // bf16 hi/lo stage images of the point MLP (DISN_PREC_BF16X3)
   int64_t tc_weights_bytes = 0;
+  void* tc_weights_f8 = nullptr;       // fp16 + e5m2 stage images (DISN_PREC_F16F8)
+  float tc_act_scale[2][4][2] = {};
   std::map<std::string, uint8_t*> enc_tc_weights;   // packed bf16 hi/lo stage images of the encoder GEMMs
 };
 

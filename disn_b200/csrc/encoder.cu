@@ -252,7 +252,7 @@ static int launch_gemm(disn_ctx* c, int mode, const float* A, const float* Bm, c
 // the shapes fit (K % 64 == 0, channels % 64 == 0); fp32 CUDA-core path otherwise (conv1_1: Cin = 3).
 static int gemm_any(disn_ctx* c, const std::string& wname, int mode, const float* A, const float* Bm, const float* bias,
                     float* C, int M, int N, int K, int relu, ConvGeom g) {
-  const bool tc_ok = c->cfg.precision == DISN_PREC_BF16X3 && K % 64 == 0 && N % 32 == 0 &&
+  const bool tc_ok = c->cfg.precision != DISN_PREC_FP32 && K % 64 == 0 && N % 32 == 0 &&
                      (mode == A_PLAIN || g.Cin % 64 == 0);
   if (!tc_ok) return launch_gemm(c, mode, A, Bm, bias, C, M, N, K, relu, g);
   uint8_t*& pk = c->enc_tc_weights[wname];

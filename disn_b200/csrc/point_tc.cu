@@ -24,8 +24,12 @@
 //     on each barrier class (profiles/*_tc_wait_trace.txt).
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <vector>
+
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -85,20 +89,56 @@ __device__ __forceinline__ TileCoord tile_coord(int64_t tile, int64_t tiles_per_
   return t;
 }
 
-// write one thread's 32 consecutive K values (hi and lo) of row p into an A-tile slot
-__device__ __forceinline__ void store_slice(uint8_t* xhi, uint8_t* xlo, int p, int h, const float* v) {
-  uint32_t hi[16], lo[16];
+// operand-format modes of the kernel
+constexpr int MODE_BF16X3 = 0;   // x = hi + lo (bf16): hi*hi + lo*hi + hi*lo, 12 kind::f16 MMAs per 64-wide K slice
+constexpr int MODE_F16F8 = 1;    // fp16 main product + two e5m2 correction products (kind::f8f6f4, twice the rate):
+                                 //   a.w ~= h(a).h(w) + e((a-h(a)).2^s1).e(w.2^-s1) + e(a.2^-s2).e((w-h(w)).2^s2), 4 + 2 + 2 MMAs
+constexpr int X8_TILE = 4096;    // 64 rows x 64 k x 1 B (SW64)
+constexpr int W8_TILE = 8192;    // 128 rows x 64 k x 1 B (SW64)
+
+// write one thread's 32 consecutive K values of row p into an A-tile slot.
+// MODE_BF16X3: x0 = bf16 hi tile, x1 = bf16 lo tile (both SW128).
+// MODE_F16F8 : x0 = fp16 tile (SW128), x1 = [e5m2((a-h).sc_lo) | e5m2(a.sc_hi)] two SW64 byte tiles.
+template <int kMode>
+__device__ __forceinline__ void store_slice(uint8_t* x0, uint8_t* x1, int p, int h, const float* v, float sc_lo,
+                                            float sc_hi) {
+  if constexpr (kMode == MODE_BF16X3) {
+    uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) tc::split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+    for (int j = 0; j < 16; ++j) tc::split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t off = tc::sw128_offset((uint32_t)p, (uint32_t)(h * 4 + q));
-    *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-    *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t off = tc::sw128_offset((uint32_t)p, (uint32_t)(h * 4 + q));
+      *reinterpret_cast<uint4*>(x0 + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+      *reinterpret_cast<uint4*>(x1 + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    }
+  } else {
+    uint32_t m[16], lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = v[2 * j], b = v[2 * j + 1];
+      const __half2 hh = __floats2half2_rn(a, b);
+      m[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      const float ra = a - __low2float(hh), rb = b - __high2float(hh);
+      const uint32_t l = __nv_cvt_float2_to_fp8x2(make_float2(ra * sc_lo, rb * sc_lo), __NV_SATFINITE, __NV_E5M2);
+      const uint32_t g = __nv_cvt_float2_to_fp8x2(make_float2(a * sc_hi, b * sc_hi), __NV_SATFINITE, __NV_E5M2);
+      if (j & 1) { lo[j >> 1] |= l << 16; hi[j >> 1] |= g << 16; }
+      else { lo[j >> 1] = l; hi[j >> 1] = g; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(x0 + tc::sw128_offset((uint32_t)p, (uint32_t)(h * 4 + q))) =
+          make_uint4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t off = tc::sw64_offset((uint32_t)p, (uint32_t)(h * 2 + q));
+      *reinterpret_cast<uint4*>(x1 + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+      *reinterpret_cast<uint4*>(x1 + X8_TILE + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+    }
   }
 }
 
-template <bool kTrace>
+template <bool kTrace, int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per_img,
                 unsigned long long* __restrict__ dbg) {
@@ -186,7 +226,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       // ===================== MMA issuer (leader CTA) =====================
       // The whole warp runs the loop so every address/descriptor is warp-uniform (uniform registers);
       // a single elected lane issues the tcgen05 instructions.
-      const uint32_t idesc = tc::make_idesc_bf16(128, 256);
+      const uint32_t idesc = (kMode == MODE_BF16X3) ? tc::make_idesc_bf16(128, 256) : tc::make_idesc_f16(128, 256);
+      const uint32_t idesc8 = tc::make_idesc_e5m2(128, 256);
       const uint32_t w_lo0 = tc::desc_lo(tc::smem_u32(s.w[0]));          // + st * (W_STAGE >> 4)
       const uint32_t x_lo0 = tc::desc_lo(tc::smem_u32(s.x[0][0]));       // + slot * (2*X_HALF >> 4), lo = + X_HALF >> 4
       const uint32_t x2_lo0 = tc::desc_lo(tc::smem_u32(s.x2[0]));
@@ -227,12 +268,24 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                 const uint32_t b_lo = b_hi + (W_TILE >> 4);
                 const long long ti = kTrace ? clock64() : 0;
                 if (tc::elect_one()) {
+                  if constexpr (kMode == MODE_BF16X3) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_lo + 2u * k, b_hi + 2u * k, idesc, 1u);
+                    for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_lo + 2u * k, b_hi + 2u * k, idesc, 1u);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
+                    for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
+                  } else {
+                    // a_hi = fp16 A tile, a_lo = e5m2 residual tile (+X8_TILE: e5m2 copy of a); b_hi = fp16 W tile,
+                    // b_lo = e5m2 copy of w (+W8_TILE: e5m2 residual of w)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) tc::mma_cg2_f8_lo(d, a_lo + 2u * k, b_lo + 2u * k, idesc8, 1u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                      tc::mma_cg2_f8_lo(d, a_lo + (X8_TILE >> 4) + 2u * k, b_lo + (W8_TILE >> 4) + 2u * k, idesc8, 1u);
+                  }
                   tc::commit_cg2(&s.wempty[st], 0b11);
                 }
                 __syncwarp();
@@ -276,7 +329,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       }
     };
     // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into activation slice `seq`
-    auto drain = [&](uint32_t col0, int t, const float* bias, uint32_t seq, bool gather) {
+    auto drain = [&](uint32_t col0, int t, const float* bias, uint32_t seq, bool gather, float sc_lo, float sc_hi) {
       const int slot = seq % NX;
       uint32_t r[32];
       tc::tmem_ld_x32(tlane + col0 + 32u * t, r);
@@ -301,7 +354,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + v[j], 0.f);
       // the slot is only needed now: its release (MMA consumption of slice seq-NX) overlaps the work above
       TIMED_WAIT(3, tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1));
-      store_slice(s.x[slot][0], s.x[slot][1], p, h, v);
+      store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, sc_lo, sc_hi);
       arrive_xfull(slot);
       if (gather && lane == 0) tc::mbar_arrive(&s.gempty[gs]);   // after the critical-path signal
     };
@@ -315,16 +368,16 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         // fold1/conv2 output (256) -> X3
         TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[0], par));
         tc::tc_fence_after_sync();
-        for (int t = 0; t < 4; ++t) drain(0u, t, sb + SB_B2, seq0 + t, false);
+        for (int t = 0; t < 4; ++t) drain(0u, t, sb + SB_B2, seq0 + t, false, job.act_scale[sidx][1][0], job.act_scale[sidx][1][1]);
         // fold1/conv3 output (512) -> X4
         TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[1], par));
         tc::tc_fence_after_sync();
-        for (int t = 0; t < 8; ++t) drain(256u, t, sb + SB_B3, seq0 + 4 + t, false);
+        for (int t = 0; t < 8; ++t) drain(256u, t, sb + SB_B3, seq0 + 4 + t, false, job.act_scale[sidx][2][0], job.act_scale[sidx][2][1]);
         // fold2/conv1 output (512) + folded image features -> X5
         TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[2], par));
         tc::tc_fence_after_sync();
         const float* b4 = sidx ? (sb + SB_B4) : (job.gbias + (int64_t)tc0.b * kHidden);
-        for (int t = 0; t < 8; ++t) drain(0u, t, b4, seq0 + 12 + t, sidx == 1);
+        for (int t = 0; t < 8; ++t) drain(0u, t, b4, seq0 + 12 + t, sidx == 1, job.act_scale[sidx][3][0], job.act_scale[sidx][3][1]);
         // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
         TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[3], par));
         tc::tc_fence_after_sync();
@@ -373,7 +426,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     const int fw = warp - 8;
     const int Wm = job.img_w, Hm = job.img_h;
 
-    auto stage_x2 = [&](const float* sb, uint32_t use) {   // use = running stream count
+    auto stage_x2 = [&](const float* sb, uint32_t use, float sc_lo, float sc_hi) {   // use = running stream count
       tc::mbar_wait(&s.x2empty, (use & 1) ^ 1);
       const float x = s.px[p], y = s.py[p], z = s.pz[p];
       float v[32];
@@ -386,7 +439,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         a = fmaf(z, sb[SB_W1 + 128 + f], a);
         v[j] = fmaxf(a, 0.f);
       }
-      store_slice(s.x2[0], s.x2[1], p, h, v);
+      store_slice<kMode>(s.x2[0], s.x2[1], p, h, v, sc_lo, sc_hi);
       tc::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -452,8 +505,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         for (int k = 0; k < 4; ++k) { s.tap_off[ft][k] = off[k]; s.tap_w[ft][k] = wg[k]; }
       }
       named_bar_sync(2, 128);
-      stage_x2(s.sb[0], (uint32_t)it * 2);
-      stage_x2(s.sb[1], (uint32_t)it * 2 + 1);
+      stage_x2(s.sb[0], (uint32_t)it * 2, job.act_scale[0][0][0], job.act_scale[0][0][1]);
+      stage_x2(s.sb[1], (uint32_t)it * 2 + 1, job.act_scale[1][0][0], job.act_scale[1][0][1]);
       // gather of the projected feature map for the local stream's fold2/conv1 epilogue
       const float* pm = job.pmap + (int64_t)b * Hm * Wm * kHidden;
       const int grp = lane >> 3, q = lane & 7;
@@ -553,24 +606,81 @@ int tc_pack_weights(disn_ctx* c) {
   DISN_REQUIRE(stage == (size_t)2 * STAGES_PER_STREAM, "internal: stage count");
   if (c->tc_weights_bytes != (int64_t)total) {
     if (c->tc_weights) cudaFree(c->tc_weights);
-    c->tc_weights = nullptr;
+    if (c->tc_weights_f8) cudaFree(c->tc_weights_f8);
+    c->tc_weights = c->tc_weights_f8 = nullptr;
     DISN_CUDA_OK(cudaMalloc(&c->tc_weights, total));
+    DISN_CUDA_OK(cudaMalloc(&c->tc_weights_f8, total));
     c->tc_weights_bytes = (int64_t)total;
   }
   DISN_CUDA_OK(cudaMemcpyAsync(c->tc_weights, img.data(), total, cudaMemcpyHostToDevice, c->stream));
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));   // ordered on the ctx stream (see conv_tc_pack)
+
+  // ---- DISN_PREC_F16F8 images: per (stage, CTA half): [fp16 W, SW128, 16 KB | e5m2(w.2^-s1), SW64, 8 KB |
+  //      e5m2((w - fp16(w)).2^s2), SW64, 8 KB].  The exponents follow the layer's weight rms (2^L) so that the
+  //      e5m2 operands (normal range 2^-14 .. 2^15, 2 mantissa bits) sit mid-range for O(1) activations:
+  //      s1 = 10 + L, s2 = 12 + L; the matching activation multipliers 2^s1 and 2^-s2 go to the kernel.
+  std::fill(img.begin(), img.end(), 0);
+  stage = 0;
+  for (int sidx = 0; sidx < 2; ++sidx) {
+    const std::string p = sidx ? "sdfprediction_imgfeat" : "sdfprediction";
+    const char* names[4] = {"/fold1/conv2/weights", "/fold1/conv3/weights", "/fold2/conv1/weights", "/fold2/conv2/weights"};
+    for (int layer = 0; layer < 4; ++layer) {
+      auto it = c->weights.find(p + names[layer]);
+      const int K = Ks[layer], N = Ns[layer];
+      std::vector<float> w((size_t)K * N);
+      DISN_CUDA_OK(cudaMemcpyAsync(w.data(), it->second.ptr, w.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+      double ss = 0;
+      for (float v : w) ss += (double)v * v;
+      const double rms = std::sqrt(ss / (double)w.size());
+      const int L = rms > 0 ? (int)std::lround(std::log2(rms)) : -4;
+      const int s1 = std::min(24, std::max(-8, 10 + L)), s2 = std::min(28, std::max(-8, 12 + L));
+      c->tc_act_scale[sidx][layer][0] = std::ldexp(1.f, s1);
+      c->tc_act_scale[sidx][layer][1] = std::ldexp(1.f, -s2);
+      for (int t = 0; t < K / 64; ++t)
+        for (int nb = 0; nb < N / 256; ++nb, ++stage)
+          for (int half = 0; half < 2; ++half) {
+            uint8_t* dst = img.data() + stage * (2 * W_STAGE) + (size_t)half * W_STAGE;
+            for (int nl = 0; nl < 128; ++nl) {
+              const int n = nb * 256 + half * 128 + nl;
+              for (int k = 0; k < 64; ++k) {
+                const float v = w[(size_t)fin_of(layer, t, k) * N + n];
+                const __half hv = __float2half_rn(v);
+                memcpy(dst + tc::sw128_offset(nl, k / 8) + (k % 8) * 2, &hv, 2);
+                const uint32_t o8 = tc::sw64_offset(nl, k / 16) + (k % 16);
+                dst[W_TILE + o8] = (uint8_t)__nv_cvt_float_to_fp8(std::ldexp(v, -s1), __NV_SATFINITE, __NV_E5M2);
+                dst[W_TILE + W8_TILE + o8] =
+                    (uint8_t)__nv_cvt_float_to_fp8(std::ldexp(v - __half2float(hv), s2), __NV_SATFINITE, __NV_E5M2);
+              }
+            }
+          }
+    }
+  }
+  DISN_CUDA_OK(cudaMemcpyAsync(c->tc_weights_f8, img.data(), total, cudaMemcpyHostToDevice, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
-int launch_point_tc(disn_ctx* c, const PointJob& job) {
-  DISN_REQUIRE(c->tc_weights != nullptr, "tensor-core weights not packed (call disn_finalize_weights)");
+template <bool kTrace, int kMode>
+static int launch_variant(disn_ctx* c, const PointJob& job, const void* wpk, int pairs, int smem, int64_t tiles_per_img,
+                          unsigned long long* dbg) {
   static bool attr_set = false;
-  const int smem = (int)sizeof(TcSmem) + 1024;
   if (!attr_set) {
-    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<kTrace, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
+  point_tc_kernel<kTrace, kMode><<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(wpk),
+                                                                          tiles_per_img, dbg);
+  return 0;
+}
+
+int launch_point_tc(disn_ctx* c, const PointJob& job_in) {
+  const bool f8 = c->cfg.precision == DISN_PREC_F16F8;
+  const void* wpk = f8 ? c->tc_weights_f8 : c->tc_weights;
+  DISN_REQUIRE(wpk != nullptr, "tensor-core weights not packed (call disn_finalize_weights)");
+  PointJob job = job_in;
+  memcpy(job.act_scale, c->tc_act_scale, sizeof(job.act_scale));
+  const int smem = (int)sizeof(TcSmem) + 1024;
   const int64_t tiles_per_img = (job.N + 2 * PTS - 1) / (2 * PTS);
   const int64_t total = tiles_per_img * job.B;
   if (total == 0) return 0;
@@ -583,12 +693,12 @@ int launch_point_tc(disn_ctx* c, const PointJob& job) {
     DISN_CUDA_OK(cudaMalloc(&dbg, (size_t)pairs * 2 * 16 * sizeof(unsigned long long)));
     DISN_CUDA_OK(cudaMemsetAsync(dbg, 0, (size_t)pairs * 2 * 16 * sizeof(unsigned long long), c->stream));
   }
-  if (trace)
-    point_tc_kernel<true><<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(c->tc_weights),
-                                                                  tiles_per_img, dbg);
-  else
-    point_tc_kernel<false><<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(c->tc_weights),
-                                                                   tiles_per_img, dbg);
+  int rc;
+  if (trace) rc = f8 ? launch_variant<true, MODE_F16F8>(c, job, wpk, pairs, smem, tiles_per_img, dbg)
+                     : launch_variant<true, MODE_BF16X3>(c, job, wpk, pairs, smem, tiles_per_img, dbg);
+  else rc = f8 ? launch_variant<false, MODE_F16F8>(c, job, wpk, pairs, smem, tiles_per_img, dbg)
+               : launch_variant<false, MODE_BF16X3>(c, job, wpk, pairs, smem, tiles_per_img, dbg);
+  if (rc) return rc;
   c->launches++;
   DISN_CUDA_OK(cudaGetLastError());
   if (trace) {   // debug only: per-role blocked cycles, averaged over CTAs

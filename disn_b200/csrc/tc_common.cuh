@@ -208,6 +208,32 @@ __device__ __forceinline__ void mma_cg2_lo(uint32_t d_tmem, uint32_t a_lo, uint3
       : "memory");
 }
 
+// ---- mixed-kind path (DISN_PREC_F16F8): fp16 main product + e5m2 correction products in one accumulator ----
+// instruction descriptor with A=B=fp16 (kind::f16) -- formats 0; for kind::f8f6f4 format 1 = E5M2, i.e. the same bits as
+// make_idesc_bf16 (cute::UMMA::InstrDescriptor: a_format [7,10), b_format [10,13)).
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_e5m2(uint32_t M, uint32_t N) { return make_idesc_bf16(M, N); }
+// K-major SWIZZLE_64B tile of 1-byte elements: rows of 64 B, 8-row groups 512 B apart (SBO=32), layout_type=4
+constexpr uint32_t kDescHiSw64 = 32u | (1u << 14) | (4u << 29);
+__host__ __device__ constexpr uint32_t sw64_offset(uint32_t row, uint32_t chunk) {
+  return (row >> 3) * 512u + (row & 7u) * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
+}
+// kind::f8f6f4, K = 32 per instruction, both operands SW64 tiles
+__device__ __forceinline__ void mma_cg2_f8_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %3, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw64), "r"(0u)
+      : "memory");
+}
+
 // swizzled byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a K-major SW128 tile
 __host__ __device__ constexpr uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);

@@ -6,9 +6,9 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import DISN_DEVICE_PTR, PREC_BF16X3, PREC_FP32, DisnConfig, check
+from ._lib import DISN_DEVICE_PTR, PREC_BF16X3, PREC_F16F8, PREC_FP32, DisnConfig, check
 
-_PREC = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3}
+_PREC = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "f16f8": PREC_F16F8}
 TAP_HW = (224, 112, 56, 28, 14)
 TAP_C = (64, 128, 256, 512, 512)
 

@@ -47,6 +47,8 @@ enum {
 enum {
   DISN_PREC_FP32 = 0,    /* CUDA-core fp32 FMA (exact restatement of the reference arithmetic) */
   DISN_PREC_BF16X3 = 1,  /* tcgen05 tensor cores, bf16 hi/lo split operands, 3 MMAs per product, fp32 accumulate */
+  DISN_PREC_F16F8 = 2,   /* tcgen05: fp16 main product + two e5m2 (kind::f8f6f4, 2x rate) correction products, fp32
+                            accumulate: 2 MMA-units per product instead of 3; activations must stay below 65504 */
 };
 
 typedef struct disn_config {
@@ -132,6 +134,10 @@ int disn_nn_distance(disn_ctx* ctx, const float* xyz1, const float* xyz2, int32_
 /* Diagnostic: one CTA-pair tcgen05 (cta_group::2) GEMM D[128x256] = A[128x64] * B[256x64]^T, `passes` times
  * accumulated; returns the raw TMEM image D_out[2 CTAs][128 lanes][128 columns]. Host pointers. */
 int disn_tc_selftest(int device, const float* A, const float* B, int passes, float* D_out);
+/* Diagnostic: mixed-kind accumulation used by DISN_PREC_F16F8 -- D = fp16(A16).fp16(B16)^T (mode bit 0) +
+ * e5m2(A8).e5m2(B8)^T (mode bit 1) into one TMEM accumulator; A8q/B8q return the e5m2 values actually used. */
+int disn_tc_selftest_mixed(int device, const float* A16, const float* B16, const float* A8, const float* B8, int mode,
+                           float* A8q, float* B8q, float* D_out);
 
 /* Diagnostic: one encoder GEMM (plain when H == 0, else the 3x3 SAME im2col view of NHWC A[M/(H*W),H,W,Cin]) through
  * the fp32 CUDA-core kernel and through the tcgen05 kernel; host pointers, outputs [M,N]. */

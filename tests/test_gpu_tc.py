@@ -152,3 +152,86 @@ def test_tc_encoder_matches_oracle(tc_engine, he_weights):
         off += c
     got = tc_engine.get_encoded(6)
     assert np.abs(got - pmap).max() <= 5e-5 * np.abs(pmap).max()
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_tc_selftest_mixed_kinds(mode):
+    """kind::f16 (fp16, SW128) and kind::f8f6f4 (e5m2, SW64) MMAs accumulating into the same TMEM tile."""
+    from disn_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(mode)
+    A16 = rng.standard_normal((128, 64)).astype(np.float32)
+    B16 = rng.standard_normal((256, 64)).astype(np.float32)
+    A8 = (rng.standard_normal((128, 64)) * 2.0 ** -6).astype(np.float32)
+    B8 = (rng.standard_normal((256, 64)) * 2.0 ** 3).astype(np.float32)
+    A8q, B8q = np.empty_like(A8), np.empty_like(B8)
+    D = np.empty((2, 128, 128), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(lib.disn_tc_selftest_mixed(0, p(A16), p(B16), p(A8), p(B8), mode, p(A8q), p(B8q), p(D)))
+    assert np.abs(A8q - A8).max() <= 0.125 * np.abs(A8).max() + 2.0 ** -17      # e5m2: 2 mantissa bits
+    ref = np.zeros((128, 256))
+    if mode & 1:
+        ref += A16.astype(np.float16).astype(np.float64) @ B16.astype(np.float16).astype(np.float64).T
+    if mode & 2:
+        ref += A8q.astype(np.float64) @ B8q.astype(np.float64).T
+    got = np.empty((128, 256), np.float64)
+    for c in range(2):
+        for h in range(2):
+            got[c * 64:(c + 1) * 64, h * 128:(h + 1) * 128] = D[c, h * 64:(h + 1) * 64, :]
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() < 2e-6 * max(1.0, np.abs(ref).max()) * 8
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DISN_PREC_F16F8: fp16 product + two e5m2 correction products
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def f8_engine(he_weights):
+    from disn_b200.engine import Engine
+    eng = Engine(device=0, precision="f16f8", max_batch=2)
+    eng.load_weights(he_weights)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 3000, 20000])
+def test_f16f8_eval_points_matches_oracle(f8_engine, he_weights, n):
+    """f16f8 path vs the fp64 oracle: |sdf - ref| <= 1e-4 (north_star tolerance)."""
+    from disn_b200 import synth
+    from oracle import disn_oracle as orc
+    imgs = synth.synthetic_images(2, seed=1234)
+    f8_engine.encode(imgs)
+    enc = orc.encode(imgs, he_weights, dtype=np.float64)
+    rng = np.random.default_rng(300 + n)
+    pts = rng.uniform(-1, 1, size=(2, n, 3)).astype(np.float32)
+    tm = np.concatenate([synth.DEMO_TRANS_MAT, synth.synthetic_trans_mats(1)], axis=0)
+    pred = f8_engine.eval_points(pts, tm)
+    nref = min(n, 3000)
+    ref = orc.decode(enc, pts[:, :nref], pts[:, :nref], tm, he_weights, dtype=np.float64)
+    err = np.abs(pred[:, :nref] - ref["pred_sdf"]).max() / orc.SDF_WEIGHT
+    print("f16f8 max |sdf - oracle64| =", err)
+    assert err <= 1e-4, err
+    if n > nref:
+        f8_engine.set_precision("fp32")
+        p32 = f8_engine.eval_points(pts, tm)
+        f8_engine.set_precision("f16f8")
+        assert np.abs(pred - p32).max() / orc.SDF_WEIGHT <= 1e-4
+
+
+def test_f16f8_full_size_grid_properties(f8_engine):
+    """257^3 grid: within 1e-4 of the fp32 CUDA-core path everywhere, deterministic, slab-invariant."""
+    from disn_b200 import synth
+    imgs = synth.synthetic_images(1)
+    f8_engine.encode(imgs)
+    tm, sp = synth.DEMO_TRANS_MAT, synth.DEMO_SDF_PARAMS
+    g1 = f8_engine.eval_grid(sp, tm, 256)
+    assert np.isfinite(g1).all()
+    np.testing.assert_array_equal(g1, f8_engine.eval_grid(sp, tm, 256))
+    slabs = [f8_engine.eval_grid(sp, tm, 256, z0=a, z1=b) for a, b in ((0, 100), (100, 257))]
+    np.testing.assert_array_equal(np.concatenate(slabs, axis=1), g1)
+    f8_engine.set_precision("fp32")
+    g32 = f8_engine.eval_grid(sp, tm, 256)
+    f8_engine.set_precision("f16f8")
+    err = float(np.abs(g1 - g32).max())
+    print("f16f8 257^3 max |sdf - fp32 path| =", err)
+    assert err <= 1e-4, err
