@@ -45,7 +45,7 @@ constexpr int W_STAGE = 2 * W_TILE;   // [W_hi | W_lo] for one (K-slice, N-block
 constexpr int X_HALF = 8192;          // 64 rows x 64 k x bf16
 constexpr int G_LD = 65;              // padded point stride of the gather ring
 constexpr int PTS = 64;               // points per CTA per tile
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 512;
 constexpr int STAGES_PER_STREAM = 33; // 1 + 8 + 16 + 8 weight stages (pair-level, 64 KB each: 2 CTA halves x [hi|lo])
 // shared-memory table of small fp32 parameters per stream
 constexpr int SB_B2 = 0, SB_B3 = 256, SB_B4 = 768, SB_B5 = 1280, SB_W6 = 1536, SB_W1 = 1792, SB_B1 = 1984, SB_STRIDE = 2048;
@@ -60,7 +60,7 @@ struct TcSmem {
   float px[PTS], py[PTS], pz[PTS];
   int tap_off[PTS][4];
   float tap_w[PTS][4];
-  float part[2][2][2][PTS];                    // [tile parity][stream][half][point]
+  float part[2][2][2][2][PTS];                 // [tile parity][stream][half][epilogue group][point]
   alignas(8) uint64_t wfull[NW];
   uint64_t wempty[NW];
   uint64_t xfull[NX];
@@ -141,7 +141,7 @@ __device__ __forceinline__ void store_slice(uint8_t* x0, uint8_t* x1, int p, int
 template <bool kTrace, int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per_img,
-                unsigned long long* __restrict__ dbg) {
+                unsigned long long* __restrict__ dbg, int expt) {
   extern __shared__ uint8_t smem_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const uint32_t cta = tc::cluster_ctarank();
@@ -157,7 +157,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     tc::mbar_init(&s.x2empty, 1);
     for (int i = 0; i < NG; ++i) { tc::mbar_init(&s.gfull[i], 4); tc::mbar_init(&s.gempty[i], 4); }
     for (int i = 0; i < 4; ++i) tc::mbar_init(&s.acc_full[i], 1);
-    tc::mbar_init(&s.acc5_free, 8);
+    tc::mbar_init(&s.acc5_free, 16);
     tc::fence_barrier_init();
   }
   for (int i = tid; i < 2 * SB_STRIDE; i += NTHREADS) {   // small parameters -> shared memory, once
@@ -194,6 +194,15 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     } else {                                            \
       call;                                             \
     }                                                   \
+  } while (0)
+
+  // timeline of one tile of CTA 0 (trace build): raw clock64 stamps, decoded by tools/tc_timeline.py
+  unsigned long long* tl = dbg ? dbg + (size_t)gridDim.x * 24 : nullptr;
+#define TL(it_, idx)                                                                         \
+  do {                                                                                       \
+    if constexpr (kTrace) {                                                                  \
+      if (blockIdx.x == 0 && (it_) == 4 && lane == 0) tl[idx] = (unsigned long long)clock64(); \
+    }                                                                                        \
   } while (0)
 
   if (warp == 0 || warp == 2 || warp == 3) {
@@ -258,6 +267,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
               }
               const uint32_t a_lo = a_hi + (X_HALF >> 4);
               tc::tc_fence_after_sync();
+              const int sl = sidx * 21 + (layer == 0 ? 0 : layer == 1 ? 1 + t : layer == 2 ? 5 + t : 13 + t);
+              TL(it, 0 + sl);                 // A slice acquired
 #pragma unroll 1
               for (int nb = 0; nb < nnb; ++nb) {
                 const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
@@ -278,13 +289,20 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                   } else {
                     // a_hi = fp16 A tile, a_lo = e5m2 residual tile (+X8_TILE: e5m2 copy of a); b_hi = fp16 W tile,
                     // b_lo = e5m2 copy of w (+W8_TILE: e5m2 residual of w)
+                    const bool x0 = !kTrace || !(expt & 1), x1 = !kTrace || !(expt & 2), x2 = !kTrace || !(expt & 4);
+                    if (x0) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
+                      for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
+                    }
+                    if (x1) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) tc::mma_cg2_f8_lo(d, a_lo + 2u * k, b_lo + 2u * k, idesc8, 1u);
+                      for (int k = 0; k < 2; ++k) tc::mma_cg2_f8_lo(d, a_lo + 2u * k, b_lo + 2u * k, idesc8, 1u);
+                    }
+                    if (x2) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                      tc::mma_cg2_f8_lo(d, a_lo + (X8_TILE >> 4) + 2u * k, b_lo + (W8_TILE >> 4) + 2u * k, idesc8, 1u);
+                      for (int k = 0; k < 2; ++k)
+                        tc::mma_cg2_f8_lo(d, a_lo + (X8_TILE >> 4) + 2u * k, b_lo + (W8_TILE >> 4) + 2u * k, idesc8, 1u);
+                    }
                   }
                   tc::commit_cg2(&s.wempty[st], 0b11);
                 }
@@ -292,29 +310,37 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                 if constexpr (kTrace) wt[1] += (unsigned long long)(clock64() - ti);
                 if (++wst == NW) { wst = 0; wph ^= 1u; }
               }
+              const long long tcm = kTrace ? clock64() : 0;
               if (tc::elect_one()) {
                 if (layer == 0) tc::commit_cg2(&s.x2empty, 0b11);
                 else tc::commit_cg2(&s.xempty[slot], 0b11);
               }
               __syncwarp();
+              if constexpr (kTrace) wt[3] += (unsigned long long)(clock64() - tcm);
+              TL(it, 64 + sl);                // slice issued + released
               if (layer != 0) { ++xseq; if (++xsl == NX) { xsl = 0; xph ^= 1u; } }
             }
+            const long long tca = kTrace ? clock64() : 0;
             if (tc::elect_one()) tc::commit_cg2(&s.acc_full[layer], 0b11);
             __syncwarp();
+            if constexpr (kTrace) wt[4] += (unsigned long long)(clock64() - tca);
+            TL(it, 128 + sidx * 4 + layer);   // layer committed
           }
         }
       }
       if (kTrace && lane == 0) {
-        unsigned long long* o = dbg + (size_t)blockIdx.x * 16;
+        unsigned long long* o = dbg + (size_t)blockIdx.x * 24;
         o[0] = (unsigned long long)(clock64() - t_role0); o[1] = wt[0]; o[3] = wt[2];
         unsigned long long act = 0;
         for (int k = 0; k < 8; ++k) { o[8 + k] = wt[6 + k]; act += wt[6 + k]; }
-        o[2] = act; o[4] = wt[1];
+        o[2] = act; o[4] = wt[1]; o[16] = wt[3]; o[17] = wt[4];
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue: TMEM -> bias/ReLU/split -> A-tile ring =====================
-    const int ew = warp - 4;
+    // two groups of four warps (one warp per TMEM lane quarter each); group eg drains the slices of its parity
+    const int eg = (warp >= 8) ? 1 : 0;
+    const int ew = warp & 3;
     const int row = ew * 32 + lane;
     const int p = row & 63, h = row >> 6;
     const uint32_t tlane = tmem + ((uint32_t)(ew * 32) << 16);
@@ -331,6 +357,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into activation slice `seq`
     auto drain = [&](uint32_t col0, int t, const float* bias, uint32_t seq, bool gather, float sc_lo, float sc_hi) {
       const int slot = seq % NX;
+      const int tli = 192 + (int)(seq % (2 * XSLOTS_PER_STREAM)) * 5, tit = (int)(seq / (2 * XSLOTS_PER_STREAM));
+      if (ew == 0) TL(tit, tli);
       uint32_t r[32];
       tc::tmem_ld_x32(tlane + col0 + 32u * t, r);
       const int f0 = fout(h, 32 * t);
@@ -340,22 +368,25 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         const float4 bq = *reinterpret_cast<const float4*>(bias + f0 + j);
         v[j] = bq.x; v[j + 1] = bq.y; v[j + 2] = bq.z; v[j + 3] = bq.w;
       }
-      int gs = 0;
+      const int gs = eg;           // gather slice t lives in ring slot t % NG == this group's parity
       if (gather) {
-        gs = gseq % NG;
-        TIMED_WAIT(5, tc::mbar_wait(&s.gfull[gs], (gseq / NG) & 1));
+        TIMED_WAIT(5, tc::mbar_wait(&s.gfull[gs], gseq & 1));
         const float* gp = s.g[gs] + (h * 32) * G_LD + p;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += gp[j * G_LD];
         ++gseq;
       }
+      if (ew == 0) TL(tit, tli + 1);
       tc::tmem_ld_wait();
+      if (ew == 0) TL(tit, tli + 2);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + v[j], 0.f);
       // the slot is only needed now: its release (MMA consumption of slice seq-NX) overlaps the work above
       TIMED_WAIT(3, tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1));
+      if (ew == 0) TL(tit, tli + 3);
       store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, sc_lo, sc_hi);
       arrive_xfull(slot);
+      if (ew == 0) TL(tit, tli + 4);
       if (gather && lane == 0) tc::mbar_arrive(&s.gempty[gs]);   // after the critical-path signal
     };
 
@@ -368,21 +399,22 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         // fold1/conv2 output (256) -> X3
         TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[0], par));
         tc::tc_fence_after_sync();
-        for (int t = 0; t < 4; ++t) drain(0u, t, sb + SB_B2, seq0 + t, false, job.act_scale[sidx][1][0], job.act_scale[sidx][1][1]);
+        for (int t = eg; t < 4; t += 2) drain(0u, t, sb + SB_B2, seq0 + t, false, job.act_scale[sidx][1][0], job.act_scale[sidx][1][1]);
         // fold1/conv3 output (512) -> X4
         TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[1], par));
         tc::tc_fence_after_sync();
-        for (int t = 0; t < 8; ++t) drain(256u, t, sb + SB_B3, seq0 + 4 + t, false, job.act_scale[sidx][2][0], job.act_scale[sidx][2][1]);
+        for (int t = eg; t < 8; t += 2) drain(256u, t, sb + SB_B3, seq0 + 4 + t, false, job.act_scale[sidx][2][0], job.act_scale[sidx][2][1]);
         // fold2/conv1 output (512) + folded image features -> X5
         TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[2], par));
         tc::tc_fence_after_sync();
         const float* b4 = sidx ? (sb + SB_B4) : (job.gbias + (int64_t)tc0.b * kHidden);
-        for (int t = 0; t < 8; ++t) drain(0u, t, b4, seq0 + 12 + t, sidx == 1, job.act_scale[sidx][3][0], job.act_scale[sidx][3][1]);
+        for (int t = eg; t < 8; t += 2) drain(0u, t, b4, seq0 + 12 + t, sidx == 1, job.act_scale[sidx][3][0], job.act_scale[sidx][3][1]);
         // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
         TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[3], par));
         tc::tc_fence_after_sync();
+        if (ew == 0) TL(it, 400 + sidx * 8 + eg * 4);
         float part = 0.f;
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 2 * eg; t < 2 * eg + 2; ++t) {
           uint32_t r[32];
           tc::tmem_ld_x32(tlane + 256u + 32u * t, r);
           const int f0 = fout(h, 32 * t);
@@ -399,15 +431,16 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
           if (cta == 0) tc::mbar_arrive(&s.acc5_free);
           else tc::mbar_arrive_cluster(&s.acc5_free, 0);
         }
-        s.part[it & 1][sidx][h][p] = part;
+        s.part[it & 1][sidx][h][eg][p] = part;
+        if (ew == 0) TL(it, 400 + sidx * 8 + eg * 4 + 1);
       }
-      named_bar_sync(1, 128);
-      if (h == 0) {
+      named_bar_sync(1, 256);
+      if (h == 0 && eg == 0) {
         const int64_t n = tc0.n0 + (int64_t)cta * PTS + p;
         if (n < job.N) {
-          const float (*pp)[2][PTS] = s.part[it & 1];
-          float rg = (pp[0][0][p] + pp[0][1][p]) + __ldg(job.g.b6);
-          float rl = (pp[1][0][p] + pp[1][1][p]) + __ldg(job.l.b6);
+          const float (*pp)[2][2][PTS] = s.part[it & 1];
+          float rg = ((pp[0][0][0][p] + pp[0][0][1][p]) + (pp[0][1][0][p] + pp[0][1][1][p])) + __ldg(job.g.b6);
+          float rl = ((pp[1][0][0][p] + pp[1][0][1][p]) + (pp[1][1][0][p] + pp[1][1][1][p])) + __ldg(job.l.b6);
           float r = rg + rl;
           if (job.tanh_out) r = tanhf(r);
           job.out_pred[(int64_t)tc0.b * job.N + n] = r * job.out_scale;
@@ -415,15 +448,15 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       }
     }
     if (kTrace && tid == 128) {
-      unsigned long long* o = dbg + (size_t)blockIdx.x * 16;
+      unsigned long long* o = dbg + (size_t)blockIdx.x * 24;
       if (cta == 1) o[4] = (unsigned long long)(clock64() - t_role0);
       o[5] = wt[3]; o[6] = wt[4]; o[7] = wt[5];
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ===================== front end: points, projection, layer 1, feature gather =====================
-    const int ft = tid - 256;
+    const int ft = tid - 384;
     const int p = ft & 63, h = ft >> 6;
-    const int fw = warp - 8;
+    const int fw = warp - 12;
     const int Wm = job.img_w, Hm = job.img_h;
 
     auto stage_x2 = [&](const float* sb, uint32_t use, float sc_lo, float sc_hi) {   // use = running stream count
@@ -664,13 +697,14 @@ int tc_pack_weights(disn_ctx* c) {
 template <bool kTrace, int kMode>
 static int launch_variant(disn_ctx* c, const PointJob& job, const void* wpk, int pairs, int smem, int64_t tiles_per_img,
                           unsigned long long* dbg) {
+  const int expt = getenv("DISN_TC_EXPT") ? atoi(getenv("DISN_TC_EXPT")) : 0;   // trace build only: skip MMA groups
   static bool attr_set = false;
   if (!attr_set) {
     DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<kTrace, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   point_tc_kernel<kTrace, kMode><<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(wpk),
-                                                                          tiles_per_img, dbg);
+                                                                          tiles_per_img, dbg, expt);
   return 0;
 }
 
@@ -690,8 +724,8 @@ int launch_point_tc(disn_ctx* c, const PointJob& job_in) {
   unsigned long long* dbg = nullptr;
   const bool trace = getenv("DISN_TC_TRACE") != nullptr;
   if (trace) {
-    DISN_CUDA_OK(cudaMalloc(&dbg, (size_t)pairs * 2 * 16 * sizeof(unsigned long long)));
-    DISN_CUDA_OK(cudaMemsetAsync(dbg, 0, (size_t)pairs * 2 * 16 * sizeof(unsigned long long), c->stream));
+    DISN_CUDA_OK(cudaMalloc(&dbg, ((size_t)pairs * 2 * 24 + 512) * sizeof(unsigned long long)));
+    DISN_CUDA_OK(cudaMemsetAsync(dbg, 0, ((size_t)pairs * 2 * 24 + 512) * sizeof(unsigned long long), c->stream));
   }
   int rc;
   if (trace) rc = f8 ? launch_variant<true, MODE_F16F8>(c, job, wpk, pairs, smem, tiles_per_img, dbg)
@@ -702,26 +736,34 @@ int launch_point_tc(disn_ctx* c, const PointJob& job_in) {
   c->launches++;
   DISN_CUDA_OK(cudaGetLastError());
   if (trace) {   // debug only: per-role blocked cycles, averaged over CTAs
-    std::vector<unsigned long long> h((size_t)pairs * 2 * 16);
+    std::vector<unsigned long long> h((size_t)pairs * 2 * 24 + 512);
     DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
     DISN_CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     cudaFree(dbg);
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = 0; p < pairs; ++p) {
-      for (int k = 0; k < 4; ++k) a[k] += (double)h[(size_t)(2 * p) * 16 + k] / pairs;                 // leader's MMA warp
-      a[4] += (double)h[(size_t)(2 * p + 1) * 16 + 4] / pairs;                                          // peer epilogue total
-      for (int k = 5; k < 8; ++k) a[k] += 0.5 * ((double)h[(size_t)(2 * p) * 16 + k] + (double)h[(size_t)(2 * p + 1) * 16 + k]) / pairs;
+      for (int k = 0; k < 4; ++k) a[k] += (double)h[(size_t)(2 * p) * 24 + k] / pairs;                 // leader's MMA warp
+      a[4] += (double)h[(size_t)(2 * p + 1) * 24 + 4] / pairs;                                          // peer epilogue total
+      for (int k = 5; k < 8; ++k) a[k] += 0.5 * ((double)h[(size_t)(2 * p) * 24 + k] + (double)h[(size_t)(2 * p + 1) * 24 + k]) / pairs;
     }
     const double tiles = (double)total / pairs;
     fprintf(stderr, "[DISN_TC_TRACE] tiles/pair=%.1f  per-tile cycles: MMA warp total=%.0f wait{weights=%.0f, act=%.0f, acc5=%.0f} | "
                     "epilogue warp total=%.0f wait{xempty=%.0f, acc_full=%.0f, gather=%.0f}\n",
             tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles, a[6] / tiles, a[7] / tiles);
+    if (const char* tlf = getenv("DISN_TC_TIMELINE")) {     // raw stamps of tile 4 of CTA 0
+      if (FILE* f = fopen(tlf, "w")) {
+        for (int i = 0; i < 512; ++i) fprintf(f, "%d %llu\n", i, h[(size_t)pairs * 2 * 24 + i]);
+        fclose(f);
+      }
+    }
     double lw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = 0; p < pairs; ++p)
-      for (int k = 0; k < 8; ++k) lw[k] += (double)h[(size_t)(2 * p) * 16 + 8 + k] / pairs / tiles;
+      for (int k = 0; k < 8; ++k) lw[k] += (double)h[(size_t)(2 * p) * 24 + 8 + k] / pairs / tiles;
     double issue = 0;
-    for (int p = 0; p < pairs; ++p) issue += (double)h[(size_t)(2 * p) * 16 + 4] / pairs / tiles;
-    fprintf(stderr, "[DISN_TC_TRACE] MMA warp time inside the 12-MMA issue blocks per tile: %.0f cycles (66 blocks)\n", issue);
+    for (int p = 0; p < pairs; ++p) issue += (double)h[(size_t)(2 * p) * 24 + 4] / pairs / tiles;
+    double cx = 0, ca = 0;
+    for (int p = 0; p < pairs; ++p) { cx += (double)h[(size_t)(2 * p) * 24 + 16] / pairs / tiles; ca += (double)h[(size_t)(2 * p) * 24 + 17] / pairs / tiles; }
+    fprintf(stderr, "[DISN_TC_TRACE] MMA warp per tile: MMA issue blocks (66) = %.0f cycles, xempty commits (40) = %.0f, acc_full commits (8) = %.0f\n", issue, cx, ca);
     fprintf(stderr, "[DISN_TC_TRACE] MMA warp activation waits per tile: global L2..L5 = %.0f %.0f %.0f %.0f | local L2..L5 = %.0f %.0f %.0f %.0f\n",
             lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
   }

@@ -185,3 +185,95 @@ extern "C" int disn_tc_stream_probe(int device) {
   fflush(stdout);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Issue-cost micro-benchmark of the synchronisation instructions on the MMA warp's path (diagnostic).
+// One warp, ITER back-to-back instances of each op; prints average cycles per op.
+// ---------------------------------------------------------------------------------------------------------
+namespace disn {
+namespace {
+
+__global__ void __launch_bounds__(32, 1) op_cost_kernel(unsigned long long* __restrict__ out) {
+  __shared__ alignas(8) uint64_t done_bar;    // phase 0 completed -> try_wait(parity 0) succeeds immediately
+  __shared__ alignas(8) uint64_t big_bar;     // huge count: arrivals never complete a phase
+  __shared__ volatile uint32_t flag;
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    tc::mbar_init(&done_bar, 1);
+    tc::mbar_init(&big_bar, 1u << 19);
+    tc::fence_barrier_init();
+    flag = 1;
+  }
+  __syncwarp();
+  if (lane == 0) tc::mbar_arrive(&done_bar);
+  __syncwarp();
+  constexpr int ITER = 64;
+  uint32_t acc = 0;
+  const uint32_t db = tc::smem_u32(&done_bar), bb = tc::smem_u32(&big_bar);
+  long long t;
+  int slot = 0;
+#define MEASURE(cond, body)                                          \
+  __syncwarp();                                                      \
+  t = clock64();                                                     \
+  if (cond) {                                                        \
+    _Pragma("unroll 1") for (int i = 0; i < ITER; ++i) { body; }     \
+  }                                                                  \
+  __syncwarp();                                                      \
+  if (lane == 0) out[slot] = (unsigned long long)(clock64() - t) / ITER; \
+  ++slot;
+
+  // 0: empty loop
+  MEASURE(true, asm volatile("" ::: "memory"));
+  // 1: try_wait (default acquire.cta), all 32 lanes
+  MEASURE(true, { uint32_t ok; asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(db), "r"(0u) : "memory"); acc += ok; });
+  // 2: try_wait, lane 0 only
+  MEASURE(lane == 0, { uint32_t ok; asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(db), "r"(0u) : "memory"); acc += ok; });
+  // 3: try_wait.relaxed.cta, all lanes
+  MEASURE(true, { uint32_t ok; asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.relaxed.cta.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(db), "r"(0u) : "memory"); acc += ok; });
+  // 4: try_wait.relaxed.cta, lane 0
+  MEASURE(lane == 0, { uint32_t ok; asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.relaxed.cta.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(db), "r"(0u) : "memory"); acc += ok; });
+  // 5: test_wait, all lanes
+  MEASURE(true, { uint32_t ok; asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(db), "r"(0u) : "memory"); acc += ok; });
+  // 6: test_wait, lane 0
+  MEASURE(lane == 0, { uint32_t ok; asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(db), "r"(0u) : "memory"); acc += ok; });
+  // 7: mbarrier.arrive lane 0
+  MEASURE(lane == 0, asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bb) : "memory"));
+  // 8: tcgen05.commit (cta_group::1, nothing outstanding), lane 0
+  MEASURE(lane == 0, asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bb) : "memory"));
+  // 9: volatile shared load, all lanes (dependent chain through acc)
+  MEASURE(true, acc += flag);
+  // 10: tcgen05.fence::after_thread_sync
+  MEASURE(true, tc::tc_fence_after_sync());
+  // 11: fence.proxy.async.shared::cta
+  MEASURE(true, tc::fence_proxy_async_smem());
+  // 12: elect_one + branch
+  MEASURE(true, if (tc::elect_one()) acc += 1);
+  // 13: try_wait all lanes followed by tcgen05 fence (the MMA warp's pattern)
+  MEASURE(true, { uint32_t ok; asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(db), "r"(0u) : "memory"); acc += ok; tc::tc_fence_after_sync(); });
+#undef MEASURE
+  if (acc == 0xFFFFFFFFu) out[63] = acc;
+}
+
+}  // namespace
+}  // namespace disn
+
+extern "C" int disn_tc_op_probe(int device) {
+  using namespace disn;
+  DISN_CUDA_OK(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  DISN_CUDA_OK(cudaMalloc(&d, 64 * sizeof(unsigned long long)));
+  DISN_CUDA_OK(cudaMemset(d, 0, 64 * sizeof(unsigned long long)));
+  op_cost_kernel<<<1, 32>>>(d);
+  DISN_CUDA_OK(cudaGetLastError());
+  DISN_CUDA_OK(cudaDeviceSynchronize());
+  unsigned long long h[64];
+  DISN_CUDA_OK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  const char* names[14] = {"empty loop", "try_wait acquire (32 lanes)", "try_wait acquire (1 lane)", "try_wait relaxed (32 lanes)",
+                           "try_wait relaxed (1 lane)", "test_wait (32 lanes)", "test_wait (1 lane)", "mbarrier.arrive (1 lane)",
+                           "tcgen05.commit idle (1 lane)", "ld.volatile.shared (32 lanes)", "tcgen05.fence::after_thread_sync",
+                           "fence.proxy.async.shared::cta", "elect.sync + branch", "try_wait + tcgen05 fence (32 lanes)"};
+  for (int i = 0; i < 14; ++i) printf("[op_probe] %-40s %llu cycles/op\n", names[i], h[i]);
+  fflush(stdout);
+  return 0;
+}

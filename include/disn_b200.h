@@ -147,6 +147,8 @@ int disn_debug_gemm(disn_ctx* ctx, const float* A, const float* Wt, const float*
 /* Diagnostic: prints the achievable L2 -> shared-memory bulk-copy streaming rate (bytes/clk/SM) for a sweep of
  * ring depths, stage sizes and cluster multicast widths (the weight-streaming pattern of the tensor-core kernel). */
 int disn_tc_stream_probe(int device);
+/* Diagnostic: prints the issue cost (cycles) of the mbarrier / tcgen05 synchronisation instructions of the MMA warp. */
+int disn_tc_op_probe(int device);
 
 /* Kernel launch counter (bench's gpu_launches): number of this library's kernels launched so far. */
 int64_t disn_launch_count(disn_ctx* ctx);
