@@ -69,7 +69,7 @@ struct TcSmem {
   uint64_t x2empty;
   uint64_t gfull[NG];
   uint64_t gempty[NG];
-  uint64_t acc_full[4];
+  uint64_t acc_full[4][2];                     // [layer][N-block]: committed right after the block's last MMAs
   uint64_t acc5_free;
   uint32_t tmem_base;
 };
@@ -114,6 +114,7 @@ __device__ __forceinline__ void store_slice(uint8_t* x0, uint8_t* x1, int p, int
     }
   } else {
     uint32_t m[16], lo[8], hi[8];
+    const __half2 sc_hi2 = __float2half2_rn(sc_hi);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float a = v[2 * j], b = v[2 * j + 1];
@@ -121,7 +122,8 @@ __device__ __forceinline__ void store_slice(uint8_t* x0, uint8_t* x1, int p, int
       m[j] = *reinterpret_cast<const uint32_t*>(&hh);
       const float ra = a - __low2float(hh), rb = b - __high2float(hh);
       const uint32_t l = __nv_cvt_float2_to_fp8x2(make_float2(ra * sc_lo, rb * sc_lo), __NV_SATFINITE, __NV_E5M2);
-      const uint32_t g = __nv_cvt_float2_to_fp8x2(make_float2(a * sc_hi, b * sc_hi), __NV_SATFINITE, __NV_E5M2);
+      const __half2 hs = __hmul2(hh, sc_hi2);      // power-of-two scale: exact up to fp16 underflow (below e5m2 precision)
+      const uint32_t g = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hs), __NV_SATFINITE, __NV_E5M2);
       if (j & 1) { lo[j >> 1] |= l << 16; hi[j >> 1] |= g << 16; }
       else { lo[j >> 1] = l; hi[j >> 1] = g; }
     }
@@ -156,7 +158,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     tc::mbar_init(&s.x2full, 8);
     tc::mbar_init(&s.x2empty, 1);
     for (int i = 0; i < NG; ++i) { tc::mbar_init(&s.gfull[i], 4); tc::mbar_init(&s.gempty[i], 4); }
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&s.acc_full[i], 1);
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&s.acc_full[i][0], 1); tc::mbar_init(&s.acc_full[i][1], 1); }
     tc::mbar_init(&s.acc5_free, 16);
     tc::fence_barrier_init();
   }
@@ -305,6 +307,9 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                     }
                   }
                   tc::commit_cg2(&s.wempty[st], 0b11);
+                  // the block's accumulator is final after its last K slice: let the epilogue start on it while the
+                  // other N-block's MMAs still run
+                  if (t == nsl - 1) tc::commit_cg2(&s.acc_full[layer][nb], 0b11);
                 }
                 __syncwarp();
                 if constexpr (kTrace) wt[1] += (unsigned long long)(clock64() - ti);
@@ -320,10 +325,6 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
               TL(it, 64 + sl);                // slice issued + released
               if (layer != 0) { ++xseq; if (++xsl == NX) { xsl = 0; xph ^= 1u; } }
             }
-            const long long tca = kTrace ? clock64() : 0;
-            if (tc::elect_one()) tc::commit_cg2(&s.acc_full[layer], 0b11);
-            __syncwarp();
-            if constexpr (kTrace) wt[4] += (unsigned long long)(clock64() - tca);
             TL(it, 128 + sidx * 4 + layer);   // layer committed
           }
         }
@@ -355,9 +356,15 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       }
     };
     // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into activation slice `seq`
-    auto drain = [&](uint32_t col0, int t, const float* bias, uint32_t seq, bool gather, float sc_lo, float sc_hi) {
+    // (accbar != nullptr: first slice this group takes from that accumulator N-block)
+    auto drain = [&](uint32_t col0, int t, const float* bias, uint32_t seq, bool gather, float sc_lo, float sc_hi,
+                     uint64_t* accbar, uint32_t accpar) {
       const int slot = seq % NX;
       const int tli = 192 + (int)(seq % (2 * XSLOTS_PER_STREAM)) * 5, tit = (int)(seq / (2 * XSLOTS_PER_STREAM));
+      if (accbar) {
+        TIMED_WAIT(4, tc::mbar_wait(accbar, accpar));
+        tc::tc_fence_after_sync();
+      }
       if (ew == 0) TL(tit, tli);
       uint32_t r[32];
       tc::tmem_ld_x32(tlane + col0 + 32u * t, r);
@@ -397,20 +404,20 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         const uint32_t seq0 = (uint32_t)it * (2 * XSLOTS_PER_STREAM) + sidx * XSLOTS_PER_STREAM;
         const uint32_t par = (uint32_t)(it * 2 + sidx) & 1;
         // fold1/conv2 output (256) -> X3
-        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[0], par));
-        tc::tc_fence_after_sync();
-        for (int t = eg; t < 4; t += 2) drain(0u, t, sb + SB_B2, seq0 + t, false, job.act_scale[sidx][1][0], job.act_scale[sidx][1][1]);
+        for (int t = eg; t < 4; t += 2)
+          drain(0u, t, sb + SB_B2, seq0 + t, false, job.act_scale[sidx][1][0], job.act_scale[sidx][1][1],
+                t == eg ? &s.acc_full[0][0] : nullptr, par);
         // fold1/conv3 output (512) -> X4
-        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[1], par));
-        tc::tc_fence_after_sync();
-        for (int t = eg; t < 8; t += 2) drain(256u, t, sb + SB_B3, seq0 + 4 + t, false, job.act_scale[sidx][2][0], job.act_scale[sidx][2][1]);
+        for (int t = eg; t < 8; t += 2)      // thread-columns [0,128) belong to N-block 0, [128,256) to N-block 1
+          drain(256u, t, sb + SB_B3, seq0 + 4 + t, false, job.act_scale[sidx][2][0], job.act_scale[sidx][2][1],
+                t == eg ? &s.acc_full[1][0] : (t == eg + 4 ? &s.acc_full[1][1] : nullptr), par);
         // fold2/conv1 output (512) + folded image features -> X5
-        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[2], par));
-        tc::tc_fence_after_sync();
         const float* b4 = sidx ? (sb + SB_B4) : (job.gbias + (int64_t)tc0.b * kHidden);
-        for (int t = eg; t < 8; t += 2) drain(0u, t, b4, seq0 + 12 + t, sidx == 1, job.act_scale[sidx][3][0], job.act_scale[sidx][3][1]);
+        for (int t = eg; t < 8; t += 2)
+          drain(0u, t, b4, seq0 + 12 + t, sidx == 1, job.act_scale[sidx][3][0], job.act_scale[sidx][3][1],
+                t == eg ? &s.acc_full[2][0] : (t == eg + 4 ? &s.acc_full[2][1] : nullptr), par);
         // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
-        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[3], par));
+        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[3][0], par));
         tc::tc_fence_after_sync();
         if (ew == 0) TL(it, 400 + sidx * 8 + eg * 4);
         float part = 0.f;
@@ -763,7 +770,8 @@ int launch_point_tc(disn_ctx* c, const PointJob& job_in) {
     for (int p = 0; p < pairs; ++p) issue += (double)h[(size_t)(2 * p) * 24 + 4] / pairs / tiles;
     double cx = 0, ca = 0;
     for (int p = 0; p < pairs; ++p) { cx += (double)h[(size_t)(2 * p) * 24 + 16] / pairs / tiles; ca += (double)h[(size_t)(2 * p) * 24 + 17] / pairs / tiles; }
-    fprintf(stderr, "[DISN_TC_TRACE] MMA warp per tile: MMA issue blocks (66) = %.0f cycles, xempty commits (40) = %.0f, acc_full commits (8) = %.0f\n", issue, cx, ca);
+    fprintf(stderr, "[DISN_TC_TRACE] MMA warp per tile: MMA issue blocks (66) = %.0f cycles, xempty commits (40) = %.0f\n", issue, cx);
+    (void)ca;
     fprintf(stderr, "[DISN_TC_TRACE] MMA warp activation waits per tile: global L2..L5 = %.0f %.0f %.0f %.0f | local L2..L5 = %.0f %.0f %.0f %.0f\n",
             lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
   }
