@@ -258,9 +258,9 @@ def run_ours(args):
         # dram bytes per launch of the point kernel from the committed `ncu --set full` capture (profiles/)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "point_kernel_traffic.json")
-        if os.path.exists(tpath) and world == 1 and args.precision == "bf16x3":
-            t = json.load(open(tpath))
-            if t.get("sdf_res") == args.res:
+        if os.path.exists(tpath) and world == 1:
+            t = json.load(open(tpath)).get(args.precision)
+            if t and t.get("sdf_res") == args.res:
                 traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
         passes = {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1)     # tensor-pipe time in bf16-rate MMA units per product
         dtype_s = {"fp32": "f32",
@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=256)
-    ap.add_argument("--precision", default=os.environ.get("DISN_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "f16f8"])
+    ap.add_argument("--precision", default=os.environ.get("DISN_PRECISION", "f16f8"), choices=["fp32", "bf16x3", "f16f8"])
     ap.add_argument("--cpu-sample", type=int, default=8192, dest="cpu_sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

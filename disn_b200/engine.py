@@ -184,6 +184,15 @@ class Engine:
         df, _, db, _ = self.nn_distance(pred, src)
         return (df.mean(axis=1) + db.mean(axis=1)) * np.float32(1000)
 
+    def f_score(self, pred, src, thresholds):
+        """test/test_f_score.py:231-236: precision / recall = fraction of sqrt NN distances (pred->src / src->pred)
+        below each threshold; F = 2PR/(P+R).  pred, src: [1,N,3] / [1,M,3].  Distances come from the CUDA NN kernel."""
+        df, _, db, _ = self.nn_distance(pred, src)
+        th = np.asarray(thresholds, np.float32)[:, None]
+        p = (np.sqrt(df).reshape(1, -1) < th).mean(axis=1)
+        r = (np.sqrt(db).reshape(1, -1) < th).mean(axis=1)
+        return p, r, 2 * p * r / np.maximum(p + r, 1e-30)
+
     # -- marching cubes -----------------------------------------------------------------------
     def marching_cubes(self, sdf, bbox, iso: float = 0.0, device_ptr: int | None = None, R: int | None = None):
         """sdf [R,R,R] (z,y,x) -> (verts [V,3] float32, faces [F,3] int32 0-based)."""

@@ -68,6 +68,9 @@ def test_nn_distance_bit_exact_vs_reference_op(engine):
     except FileNotFoundError:
         pass
     np.testing.assert_allclose(engine.chamfer_x1000(a, b), mo.chamfer_x1000(a, b), rtol=1e-6)
+    th = [0.005, 0.01, 0.02, 0.05, 0.1]
+    for got, want in zip(engine.f_score(a[:1], b[:1], th), mo.precision_recall_f(a[:1], b[:1], th)):
+        np.testing.assert_array_equal(got, want)        # distances are bit-identical, so the counts are
     from disn_b200._lib import DisnError
     with pytest.raises(DisnError):
         engine.nn_distance(a[:, :0], b)                     # empty set: loud error like the op's shape checks
