@@ -46,6 +46,7 @@ constexpr int X_HALF = 8192;          // 64 rows x 64 k x bf16
 constexpr int G_LD = 65;              // padded point stride of the gather ring
 constexpr int PTS = 64;               // points per CTA per tile
 constexpr int NTHREADS = 512;
+constexpr int FIRST_L0_POS = 57;        // position of the even stream's L0 stage in the per-tile consumption cycle
 constexpr int STAGES_PER_STREAM = 33; // 1 + 8 + 16 + 8 weight stages (pair-level, 64 KB each: 2 CTA halves x [hi|lo])
 // shared-memory table of small fp32 parameters per stream
 constexpr int SB_B2 = 0, SB_B3 = 256, SB_B4 = 768, SB_B5 = 1280, SB_W6 = 1536, SB_W1 = 1792, SB_B1 = 1984, SB_STRIDE = 2048;
@@ -57,9 +58,9 @@ struct TcSmem {
   alignas(1024) uint8_t x2[2][X_HALF];         // fold1/conv1 output (layer-2 A operand) written by the front end
   float g[NG][64 * G_LD];                      // gathered image features [h*32+j][point]
   float sb[2][SB_STRIDE];                      // per-stream small parameters (biases, fold2/conv5, fold1/conv1)
-  float px[PTS], py[PTS], pz[PTS];
-  int tap_off[PTS][4];
-  float tap_w[PTS][4];
+  float px[2][PTS], py[2][PTS], pz[2][PTS];    // by tile parity (the front end runs one tile ahead for fold1/conv1)
+  int tap_off[2][PTS][4];
+  float tap_w[2][PTS][4];
   float part[2][2][2][2][PTS];                 // [tile parity][stream][half][epilogue group][point]
   alignas(8) uint64_t wfull[NW];
   uint64_t wempty[NW];
@@ -79,6 +80,13 @@ __host__ __device__ constexpr int fout(int h, int c) { return (c / 128) * 256 + 
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// TMEM column base of the accumulator written by tensor-core layer `layer` (0..3) of a stream with parity q.
+// Even streams: acc2 [128,256) acc3 [256,512) acc4 [0,256) acc5 [256,384); odd streams use the mirror image (^256), so the
+// NEXT stream's first accumulator always has 128 free columns while the current stream's last two layers are resident.
+__host__ __device__ constexpr uint32_t acc_col(int layer, int q) {
+  return (layer == 0 ? 128u : (layer == 2 ? 0u : 256u)) ^ ((uint32_t)q << 8);
 }
 
 struct TileCoord { int b; int64_t n0; };
@@ -220,7 +228,14 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       for (uint32_t g = pw; g < total_stages; g += NW) {
         const uint32_t use = g / NW;
         tc::mbar_wait(&s.wempty[pw], (use & 1) ^ 1);
-        const uint8_t* src = wpk + (size_t)(g % (2 * STAGES_PER_STREAM)) * (2 * W_STAGE) + (size_t)cta * W_STAGE +
+        // consumption order -> position in the packed per-tile cycle; the last tile has no "next stream" L0 stage
+        uint32_t img_stage = FIRST_L0_POS;
+        if (g > 0) {
+          const uint32_t cidx = g - 1, last0 = (uint32_t)(my_tiles - 1) * (2 * STAGES_PER_STREAM);
+          img_stage = cidx % (2 * STAGES_PER_STREAM);
+          if (cidx >= last0 && cidx - last0 >= (uint32_t)FIRST_L0_POS) img_stage = cidx - last0 + 1;
+        }
+        const uint8_t* src = wpk + (size_t)img_stage * (2 * W_STAGE) + (size_t)cta * W_STAGE +
                              (size_t)lane * W_TILE;
         tc::bulk_g2s(s.w[pw] + lane * W_TILE, src, W_TILE, &s.wfull[pw]);
         tc::mbar_wait(&s.wfull[pw], use & 1);     // leader: own bytes + peer relay; peer: own bytes
@@ -245,14 +260,23 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       uint32_t xseq = 0, nstream = 0;
       uint32_t wst = 0, wph = 0;      // weight ring slot / phase parity
       uint32_t xsl = 0, xph = 0;      // activation ring slot / phase parity
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int sidx = 0; sidx < 2; ++sidx, ++nstream) {
+      // Issue order (streams skewed by one layer): L0(0); then per stream n: L1(n) L2(n) L0(n+1) L3(n).  The next stream's
+      // first layer is tiny (one stage); hoisting it lets its drain overlap L3(n)'s MMAs, so L1(n+1) follows L3(n)
+      // without the accumulator round trip.
+      const int nstreams = 2 * my_tiles;
+      for (int grp = -1; grp < nstreams; ++grp) {
 #pragma unroll 1
-          for (int layer = 0; layer < 4; ++layer) {
+        for (int q = 0; q < 4; ++q) {
+          const int layer = (q == 0) ? 1 : (q == 1 ? 2 : (q == 2 ? 0 : 3));
+          const int sn = (q == 2) ? grp + 1 : grp;
+          if (sn < 0 || sn >= nstreams) continue;
+          nstream = (uint32_t)sn;
+          const int sidx = sn & 1, it = sn >> 1;
+          {
             const int nsl = (layer == 0) ? 1 : (layer == 1 ? 4 : 8);
             const int nnb = (layer == 1 || layer == 2) ? 2 : 1;
-            const uint32_t colbase = (layer & 1) ? 256u : 0u;
-            if (layer == 1 && nstream > 0) {   // acc3 overwrites the columns the previous stream's acc5 used
+            const uint32_t colbase = acc_col(layer, sidx);
+            if (layer == 2 && nstream > 0) {   // acc4 overwrites the columns the previous stream's acc5 used
               TIMED_WAIT(2, tc::mbar_wait(&s.acc5_free, (nstream - 1) & 1));
               tc::tc_fence_after_sync();
             }
@@ -397,25 +421,37 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       if (gather && lane == 0) tc::mbar_arrive(&s.gempty[gs]);   // after the critical-path signal
     };
 
-    for (int it = 0; it < my_tiles; ++it) {
+    // Per stream n (running index, parity = stream kind and TMEM mirror): X3 <- acc2, X4 <- acc3, X5 <- acc4, final <- acc5.
+    // The MMA warp issues L0(n+1) before L3(n), so acc2 of the next stream is complete early: its X3 slices are produced
+    // BEFORE this stream's final layer, and L1(n+1) can follow L3(n) on the tensor pipe without waiting for a drain.
+    const int nstreams = 2 * my_tiles;
+    auto drain_x3 = [&](int sn) {
+      const int sidx = sn & 1;
+      const float* sb = s.sb[sidx];
+      const uint32_t seq0 = (uint32_t)sn * XSLOTS_PER_STREAM, par = (uint32_t)sn & 1;
+      for (int t = eg; t < 4; t += 2)
+        drain(acc_col(0, sidx), t, sb + SB_B2, seq0 + t, false, job.act_scale[sidx][1][0], job.act_scale[sidx][1][1],
+              t == eg ? &s.acc_full[0][0] : nullptr, par);
+    };
+    if (nstreams > 0) drain_x3(0);
+    for (int sn = 0; sn < nstreams; ++sn) {
+      const int sidx = sn & 1, it = sn >> 1;
       const TileCoord tc0 = tile_coord((int64_t)pair + (int64_t)it * num_pairs, tiles_per_img);
-      for (int sidx = 0; sidx < 2; ++sidx) {
+      {
         const float* sb = s.sb[sidx];
-        const uint32_t seq0 = (uint32_t)it * (2 * XSLOTS_PER_STREAM) + sidx * XSLOTS_PER_STREAM;
-        const uint32_t par = (uint32_t)(it * 2 + sidx) & 1;
-        // fold1/conv2 output (256) -> X3
-        for (int t = eg; t < 4; t += 2)
-          drain(0u, t, sb + SB_B2, seq0 + t, false, job.act_scale[sidx][1][0], job.act_scale[sidx][1][1],
-                t == eg ? &s.acc_full[0][0] : nullptr, par);
+        const uint32_t seq0 = (uint32_t)sn * XSLOTS_PER_STREAM;
+        const uint32_t par = (uint32_t)sn & 1;
         // fold1/conv3 output (512) -> X4
         for (int t = eg; t < 8; t += 2)      // thread-columns [0,128) belong to N-block 0, [128,256) to N-block 1
-          drain(256u, t, sb + SB_B3, seq0 + 4 + t, false, job.act_scale[sidx][2][0], job.act_scale[sidx][2][1],
+          drain(acc_col(1, sidx), t, sb + SB_B3, seq0 + 4 + t, false, job.act_scale[sidx][2][0], job.act_scale[sidx][2][1],
                 t == eg ? &s.acc_full[1][0] : (t == eg + 4 ? &s.acc_full[1][1] : nullptr), par);
         // fold2/conv1 output (512) + folded image features -> X5
         const float* b4 = sidx ? (sb + SB_B4) : (job.gbias + (int64_t)tc0.b * kHidden);
         for (int t = eg; t < 8; t += 2)
-          drain(0u, t, b4, seq0 + 12 + t, sidx == 1, job.act_scale[sidx][3][0], job.act_scale[sidx][3][1],
+          drain(acc_col(2, sidx), t, b4, seq0 + 12 + t, sidx == 1, job.act_scale[sidx][3][0], job.act_scale[sidx][3][1],
                 t == eg ? &s.acc_full[2][0] : (t == eg + 4 ? &s.acc_full[2][1] : nullptr), par);
+        // next stream: fold1/conv2 output (256) -> X3 (its accumulator was filled before this stream's last layer)
+        if (sn + 1 < nstreams) drain_x3(sn + 1);
         // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
         TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[3][0], par));
         tc::tc_fence_after_sync();
@@ -423,7 +459,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         float part = 0.f;
         for (int t = 2 * eg; t < 2 * eg + 2; ++t) {
           uint32_t r[32];
-          tc::tmem_ld_x32(tlane + 256u + 32u * t, r);
+          tc::tmem_ld_x32(tlane + acc_col(3, sidx) + 32u * t, r);
           const int f0 = fout(h, 32 * t);
           tc::tmem_ld_wait();
 #pragma unroll
@@ -441,6 +477,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         s.part[it & 1][sidx][h][eg][p] = part;
         if (ew == 0) TL(it, 400 + sidx * 8 + eg * 4 + 1);
       }
+      if (sidx == 0) continue;
       named_bar_sync(1, 256);
       if (h == 0 && eg == 0) {
         const int64_t n = tc0.n0 + (int64_t)cta * PTS + p;
@@ -467,8 +504,9 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
     const int Wm = job.img_w, Hm = job.img_h;
 
     auto stage_x2 = [&](const float* sb, uint32_t use, float sc_lo, float sc_hi) {   // use = running stream count
+      const int pb = (use >> 1) & 1;                       // tile parity of the point buffers
       tc::mbar_wait(&s.x2empty, (use & 1) ^ 1);
-      const float x = s.px[p], y = s.py[p], z = s.pz[p];
+      const float x = s.px[pb][p], y = s.py[pb][p], z = s.pz[pb][p];
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -488,10 +526,12 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       }
     };
 
-    for (int it = 0; it < my_tiles; ++it) {
+    // query points, projection and bilinear taps of tile `it` -> parity buffers
+    auto compute_points = [&](int it) {
       const TileCoord tc0 = tile_coord((int64_t)pair + (int64_t)it * num_pairs, tiles_per_img);
       const int b = tc0.b;
-      named_bar_sync(2, 128);
+      const int pb = it & 1;
+      named_bar_sync(2, 128);          // every front-end thread is done with this parity's previous contents
       if (ft < PTS) {
         const int64_t n = tc0.n0 + (int64_t)cta * PTS + ft;
         float x = 0.f, y = 0.f, z = 0.f, xr = 0.f, yr = 0.f, zr = 0.f;
@@ -520,7 +560,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         const float q2 = fmaf(z, T[8], fmaf(y, T[5], x * T[2])) + T[11];
         const float u = fminf(job.clamp_max, fmaxf(0.f, q0 / q2));
         const float v = fminf(job.clamp_max, fmaxf(0.f, q1 / q2));
-        s.px[ft] = xr; s.py[ft] = yr; s.pz[ft] = zr;
+        s.px[pb][ft] = xr; s.py[pb][ft] = yr; s.pz[pb][ft] = zr;
         if (job.out_uv && n < job.N) {
           float* o = job.out_uv + ((int64_t)b * job.N + n) * 2;
           o[0] = u; o[1] = v;
@@ -542,11 +582,26 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { s.tap_off[ft][k] = off[k]; s.tap_w[ft][k] = wg[k]; }
+        for (int k = 0; k < 4; ++k) { s.tap_off[pb][ft][k] = off[k]; s.tap_w[pb][ft][k] = wg[k]; }
       }
       named_bar_sync(2, 128);
-      stage_x2(s.sb[0], (uint32_t)it * 2, job.act_scale[0][0][0], job.act_scale[0][0][1]);
+    };
+
+    // fold1/conv1 of a stream is staged one stream ahead of the MMAs (the MMA warp issues L0(n+1) before L3(n)), so the
+    // next tile's points are computed before this tile's gather
+    if (my_tiles > 0) {
+      compute_points(0);
+      stage_x2(s.sb[0], 0u, job.act_scale[0][0][0], job.act_scale[0][0][1]);
+    }
+    for (int it = 0; it < my_tiles; ++it) {
+      const TileCoord tc0 = tile_coord((int64_t)pair + (int64_t)it * num_pairs, tiles_per_img);
+      const int b = tc0.b;
+      const int pb = it & 1;
       stage_x2(s.sb[1], (uint32_t)it * 2 + 1, job.act_scale[1][0][0], job.act_scale[1][0][1]);
+      if (it + 1 < my_tiles) {
+        compute_points(it + 1);
+        stage_x2(s.sb[0], (uint32_t)it * 2 + 2, job.act_scale[0][0][0], job.act_scale[0][0][1]);
+      }
       // gather of the projected feature map for the local stream's fold2/conv1 epilogue
       const float* pm = job.pmap + (int64_t)b * Hm * Wm * kHidden;
       const int grp = lane >> 3, q = lane & 7;
@@ -566,8 +621,8 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
             pts[u] = pt;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int off = s.tap_off[pt][k];
-              wg[u][k] = s.tap_w[pt][k];          // zero for taps outside the map
+              const int off = s.tap_off[pb][pt][k];
+              wg[u][k] = s.tap_w[pb][pt][k];          // zero for taps outside the map
               const float* src = pm + (off >= 0 ? off : 0);
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh)
@@ -611,6 +666,10 @@ inline int fin_of(int layer, int t, int k) {
 
 // Pack both streams' tensor-core layers into the kernel's B-operand stage images:
 //   for stream, layer, slice t, N-block nb : CTA half c : part (hi, lo) : 16 KB [128 rows n][64 k] SW128 bf16
+// first position of (stream kind, layer) in the per-tile weight consumption cycle of the MMA warp:
+//   G.L1(8) G.L2(16) L.L0(1) G.L3(8) L.L1(8) L.L2(16) G.L0(1) L.L3(8)      (L0 of the next stream is issued before L3)
+static const int kCyclePos[2][4] = {{FIRST_L0_POS, 0, 8, 25}, {24, 33, 41, 58}};
+
 int tc_pack_weights(disn_ctx* c) {
   static const int Ks[4] = {64, 256, 512, 512}, Ns[4] = {256, 512, 512, 256};
   const size_t total = (size_t)2 * STAGES_PER_STREAM * 2 * W_STAGE;
@@ -630,7 +689,8 @@ int tc_pack_weights(disn_ctx* c) {
         for (int nb = 0; nb < N / 256; ++nb, ++stage)
           for (int part = 0; part < 2; ++part)
             for (int half = 0; half < 2; ++half) {
-              uint8_t* dst = img.data() + stage * (2 * W_STAGE) + (size_t)half * W_STAGE + (size_t)part * W_TILE;
+              const size_t pos = (size_t)kCyclePos[sidx][layer] + (size_t)(t * (N / 256) + nb);
+              uint8_t* dst = img.data() + pos * (2 * W_STAGE) + (size_t)half * W_STAGE + (size_t)part * W_TILE;
               for (int nl = 0; nl < 128; ++nl) {
                 const int n = nb * 256 + half * 128 + nl;
                 for (int k = 0; k < 64; ++k) {
@@ -680,7 +740,8 @@ int tc_pack_weights(disn_ctx* c) {
       for (int t = 0; t < K / 64; ++t)
         for (int nb = 0; nb < N / 256; ++nb, ++stage)
           for (int half = 0; half < 2; ++half) {
-            uint8_t* dst = img.data() + stage * (2 * W_STAGE) + (size_t)half * W_STAGE;
+            const size_t pos = (size_t)kCyclePos[sidx][layer] + (size_t)(t * (N / 256) + nb);
+            uint8_t* dst = img.data() + pos * (2 * W_STAGE) + (size_t)half * W_STAGE;
             for (int nl = 0; nl < 128; ++nl) {
               const int n = nb * 256 + half * 128 + nl;
               for (int k = 0; k < 64; ++k) {
