@@ -334,18 +334,14 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
                   // the block's accumulator is final after its last K slice: let the epilogue start on it while the
                   // other N-block's MMAs still run
                   if (t == nsl - 1) tc::commit_cg2(&s.acc_full[layer][nb], 0b11);
+                  if (nb == nnb - 1) {               // the slice's A tile is free once all of its MMAs retire
+                    if (layer == 0) tc::commit_cg2(&s.x2empty, 0b11);
+                    else tc::commit_cg2(&s.xempty[slot], 0b11);
+                  }
                 }
-                __syncwarp();
                 if constexpr (kTrace) wt[1] += (unsigned long long)(clock64() - ti);
                 if (++wst == NW) { wst = 0; wph ^= 1u; }
               }
-              const long long tcm = kTrace ? clock64() : 0;
-              if (tc::elect_one()) {
-                if (layer == 0) tc::commit_cg2(&s.x2empty, 0b11);
-                else tc::commit_cg2(&s.xempty[slot], 0b11);
-              }
-              __syncwarp();
-              if constexpr (kTrace) wt[3] += (unsigned long long)(clock64() - tcm);
               TL(it, 64 + sl);                // slice issued + released
               if (layer != 0) { ++xseq; if (++xsl == NX) { xsl = 0; xph ^= 1u; } }
             }
@@ -831,7 +827,8 @@ int launch_point_tc(disn_ctx* c, const PointJob& job_in) {
     for (int p = 0; p < pairs; ++p) issue += (double)h[(size_t)(2 * p) * 24 + 4] / pairs / tiles;
     double cx = 0, ca = 0;
     for (int p = 0; p < pairs; ++p) { cx += (double)h[(size_t)(2 * p) * 24 + 16] / pairs / tiles; ca += (double)h[(size_t)(2 * p) * 24 + 17] / pairs / tiles; }
-    fprintf(stderr, "[DISN_TC_TRACE] MMA warp per tile: MMA issue blocks (66) = %.0f cycles, xempty commits (40) = %.0f\n", issue, cx);
+    fprintf(stderr, "[DISN_TC_TRACE] MMA warp per tile: MMA issue + commit blocks (66) = %.0f cycles\n", issue);
+    (void)cx;
     (void)ca;
     fprintf(stderr, "[DISN_TC_TRACE] MMA warp activation waits per tile: global L2..L5 = %.0f %.0f %.0f %.0f | local L2..L5 = %.0f %.0f %.0f %.0f\n",
             lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
