@@ -74,3 +74,12 @@ def test_nn_distance_bit_exact_vs_reference_op(engine):
     from disn_b200._lib import DisnError
     with pytest.raises(DisnError):
         engine.nn_distance(a[:, :0], b)                     # empty set: loud error like the op's shape checks
+
+
+def test_nn_distance_matches_reference_golden(engine, golden):
+    """CUDA kernel vs outputs of the reference's own CPU op (committed fixture; the GPU box has no /root/reference)."""
+    g = golden["nn_distance_ref"]
+    for name in ("rand", "single", "lattice"):
+        got = engine.nn_distance(g[name + "_xyz1"], g[name + "_xyz2"])
+        for arr, key in zip(got, ("_dist1", "_idx1", "_dist2", "_idx2")):
+            np.testing.assert_array_equal(arr, g[name + key], err_msg=name + key)

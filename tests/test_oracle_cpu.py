@@ -132,3 +132,13 @@ def test_rotation_from_ortho6d_is_orthonormal_and_right_handed():
     # already-orthonormal input is reproduced
     eye6 = np.array([[1., 0, 0, 0, 1, 0]])
     np.testing.assert_allclose(orc.rotation_from_ortho6d(eye6)[0], np.eye(3), atol=0)
+
+
+def test_nn_distance_oracle_matches_reference_golden(golden):
+    """tests/golden/nn_distance_ref.npz holds outputs of the reference's own CPU op (tf_nndistance.cpp compiled in place)."""
+    from oracle import metrics_oracle as mo
+    g = golden["nn_distance_ref"]
+    for name in ("rand", "single", "lattice"):
+        got = mo.nn_distance(g[name + "_xyz1"], g[name + "_xyz2"])
+        for arr, key in zip(got, ("_dist1", "_idx1", "_dist2", "_idx2")):
+            np.testing.assert_array_equal(arr, g[name + key], err_msg=name + key)
