@@ -235,3 +235,25 @@ def test_f16f8_full_size_grid_properties(f8_engine):
     err = float(np.abs(g1 - g32).max())
     print("f16f8 257^3 max |sdf - fp32 path| =", err)
     assert err <= 1e-4, err
+
+
+def test_res512_grid_config4(f8_engine):
+    """BASELINE config 4 shape (--sdf_res 512: 513^3 = 135 005 697 points, 540 MB of SDF): finite, identical under a
+    different slab decomposition, and within 1e-4 of the fp32 CUDA-core path on sampled planes."""
+    from disn_b200 import synth
+    imgs = synth.synthetic_images(1)
+    f8_engine.encode(imgs)
+    tm, sp = synth.DEMO_TRANS_MAT, synth.DEMO_SDF_PARAMS
+    R = 513
+    g = f8_engine.eval_grid(sp, tm, 512)
+    assert g.shape == (1, R, R, R) and np.isfinite(g).all()
+    top = f8_engine.eval_grid(sp, tm, 512, z0=0, z1=200)
+    np.testing.assert_array_equal(top, g[:, :200])
+    del top
+    f8_engine.set_precision("fp32")
+    try:
+        for z in (0, 256, 511):
+            ref = f8_engine.eval_grid(sp, tm, 512, z0=z, z1=z + 2)
+            assert float(np.abs(ref - g[:, z:z + 2]).max()) <= 1e-4
+    finally:
+        f8_engine.set_precision("f16f8")
