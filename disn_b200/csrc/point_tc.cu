@@ -1,27 +1,37 @@
-// Fused per-point SDF kernel on tcgen05 tensor cores (DISN_PREC_BF16X3), sm_100a.
+// Fused per-point SDF kernel on tcgen05 tensor cores (DISN_PREC_BF16X3 / DISN_PREC_F16F8), sm_100a.
 //
 // Same math as point_fp32.cu (projection -> gather of the folded feature map -> two point-MLP streams
 // -> sum; models/model_normalization.py:241-251,169-206, models/sdfnet.py:69-92,171-190), but the four
-// wide layers of each stream run on the 5th-gen tensor cores.  To hold the reference's 1e-4 bar every
-// fp32 operand is split x = hi + lo (two bf16) and each product is three MMAs (hi*hi + lo*hi + hi*lo)
-// accumulated in fp32 in TMEM (error ~2^-17 per operand instead of bf16's 2^-9).
+// wide layers of each stream run on the 5th-gen tensor cores.  To hold the reference's 1e-4 bar the fp32 operands
+// are split (template parameter kMode):
+//   MODE_BF16X3  x = hi + lo (two bf16), each product = 3 kind::f16 MMAs (hi*hi + lo*hi + hi*lo), error ~2^-17;
+//   MODE_F16F8   fp16 main product + two e5m2 first-order correction products (kind::f8f6f4, twice the rate) into the
+//                same fp32 accumulator in TMEM: 2 MMA-units per product instead of 3.
 //
-// Organisation (one CTA pair = one cluster of 2, cta_group::2, UMMA M=128 x N=256 x K=16):
+// Organisation (one CTA pair = one cluster of 2, cta_group::2, UMMA M=128 x N=256 x K=16|32):
 //   * a pair-tile is 128 query points, 64 per CTA (the 2x2 datapath keeps a 512-wide fp32 layer output
 //     for 64 points in 256 TMEM columns, so one layer's input and output accumulators fit in TMEM);
 //   * activations never leave the SM: layer l's accumulator is drained 32 columns at a time by the
-//     epilogue warps (bias / folded image features, ReLU, bf16 hi/lo split) into a 3-slot ring of
-//     K-major 128B-swizzled A tiles that layer l+1's MMAs consume (K-outer), so MMA and epilogue pipeline;
+//     epilogue warps (bias / folded image features, ReLU, operand split) into a 3-slot ring of
+//     K-major swizzled A tiles that layer l+1's MMAs consume (K-outer), so MMA and epilogue pipeline; for the 512-wide
+//     layers each N-block has its own "accumulator complete" barrier, so draining starts while the other block runs;
+//   * the two streams are skewed by one layer: the MMA warp issues L0 of stream n+1 (one stage) before L3 of stream n,
+//     into the 128 TMEM columns that are free then (even/odd streams use mirrored column maps, acc_col()), so the next
+//     stream's first drain overlaps this stream's last layer; the front end stages fold1/conv1 one stream ahead;
 //   * weights are pre-split, pre-permuted and pre-swizzled on the host into the exact shared-memory images the
-//     B operand needs ([W_hi | W_lo] = 32 KB per (K-slice, N-block) and CTA) and streamed by the bulk-copy engine
-//     (cp.async.bulk) through a 3-slot mbarrier ring; each CTA loads only its half of every B tile, the peer
-//     relays its arrival to the leader.  An mbarrier operation costs the issuing thread ~200 cycles, so each
-//     ring slot has its own producer warp and the stage is as large as shared memory allows;
+//     B operand needs (32 KB per (K-slice, N-block) and CTA), packed in the MMA warp's consumption order, and streamed
+//     by the bulk-copy engine (cp.async.bulk) through a 3-slot mbarrier ring; each CTA loads only its half of every
+//     B tile, the peer relays its arrival to the leader.  On a busy SM an mbarrier operation costs the issuing thread
+//     100-250 cycles, so each ring slot has its own producer warp and the stage is as large as shared memory allows;
 //   * warp roles: 0,2,3 weight producers (2 also allocates TMEM), 1 MMA issuer (leader CTA; warp-uniform loop,
-//     one elected lane issues), 4-7 epilogue (one TMEM lane each), 8-11 front end (points, projection,
-//     layer 1, bilinear gather of the projected feature map into a shared-memory ring);
+//     one elected lane issues), 4-11 epilogue in two groups taking alternate slices (one warp per TMEM lane quarter
+//     in each group), 12-15 front end (points, projection, layer 1, bilinear gather of the projected feature map into
+//     a shared-memory ring);
+//   * every mbarrier is waited on, phase after phase, by the same agent(s): a parity wait is only meaningful for a
+//     waiter that has observed every earlier phase of that barrier (tools/tc_protocol_sim.py models the protocol);
 //   * DISN_TC_TRACE=1 runs an instrumented instantiation that accounts the cycles every role spends blocked
-//     on each barrier class (profiles/*_tc_wait_trace.txt).
+//     on each barrier class (profiles/*_tc_wait_trace.txt); DISN_TC_TIMELINE=<file> adds a one-tile event timeline
+//     (tools/tc_timeline.py), DISN_TC_EXPT=<mask> skips MMA groups in the instrumented build.
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>

@@ -1,0 +1,32 @@
+"""The mbarrier protocol of the tensor-core point kernel, checked on a discrete-event model (tools/tc_protocol_sim.py):
+no deadlock, no parity wait that skipped or overran a phase, every MMA reads the ring contents it expects, no accumulator
+overwritten while it is being drained -- under randomised operation latencies.  Broken variants must be caught."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import tc_protocol_sim as sim  # noqa: E402
+
+
+@pytest.mark.parametrize("tiles", [1, 2, 5])
+def test_kernel_protocol_is_sound_under_random_schedules(tiles):
+    for seed in range(40):
+        sim.simulate(tiles, seed)
+
+
+def test_unskewed_epilogue_order_is_also_legal():
+    for seed in range(10):
+        sim.simulate(3, seed, "x3_after_final")
+
+
+@pytest.mark.parametrize("mutation", ["no_xempty_wait", "no_wempty_wait", "no_acc_wait"])
+def test_broken_protocols_are_detected(mutation):
+    caught = 0
+    for seed in range(10):
+        try:
+            sim.simulate(3, seed, mutation)
+        except AssertionError:
+            caught += 1
+    assert caught == 10, (mutation, caught)
