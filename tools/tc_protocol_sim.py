@@ -13,16 +13,40 @@ latencies, and checks:
   * no accumulator region is written while an overlapping older accumulator still has undrained slices.
 One CTA of the pair is modelled (arrival counts that come from both CTAs are halved; the peer adds latency only).
 
-    python tools/tc_protocol_sim.py [tiles] [schedules]
+It doubles as a coarse performance model: the operation costs in PARAMS start from the ones measured on B200 (DESIGN.md
+4.1: op-cost probe, wait traces, one-tile timeline) and are tuned so that the model reproduces the measured cycles per tile
+and blocked-time split of the shipped kernel within ~10 % (f16f8: 58.7 K vs 59.9 K measured; bf16x3: see --mode), `report()` prints cycles per tile and the per-agent blocked time in the
+same classes as DISN_TC_TRACE, and `--set key=value` / `--mode` explore what-ifs (ring depths, operand mode, faster
+epilogue ...) before spending GPU time on them.
+
+    python tools/tc_protocol_sim.py [--tiles N] [--schedules N] [--mode f16f8|bf16x3] [--set key=value ...] [--report]
 """
+import argparse
 import heapq
 import random
-import sys
 
-NW, NX, NG = 3, 3, 2
 SLICES = {0: 1, 1: 4, 2: 8, 3: 8}          # K slices per tensor-core layer (L0..L3 = fold1/conv2 .. fold2/conv2)
 NNB = {0: 1, 1: 2, 2: 2, 3: 1}
 XS = 20                                     # ring slices per stream (X3: 4, X4: 8, X5: 8); X2 has its own slot
+
+PARAMS = dict(
+    NW=3, NX=3, NG=2,
+    op=100,            # an mbarrier try_wait that succeeds at once / an arrive, on a busy SM
+    commit=150,        # tcgen05.commit
+    wake=150,          # arrival -> blocked waiter running again (poll + wake-up), incl. the remote arrive of the peer CTA
+    mma_issue=112,     # 8 MMA instructions of one stage
+    mma_exec=512,      # tensor-pipe time of one stage (8 x 64 cycles); 768 for bf16x3 (12 MMAs)
+    stage_misc=200,    # fences, elect, descriptor/ring bookkeeping per stage
+    w_copy=600,        # bulk copy L2 -> smem (32 KB as 2 x 16 KB) issue -> complete_tx
+    w_relay=150,       # peer CTA observes its half and arrives on the leader's barrier
+    prod_issue=100,    # producer: slot release observed -> copies issued
+    drain_pre=250,     # tcgen05.ld + bias (+ gather add) + ReLU
+    drain_post=800,    # operand split, 8 x 16 B stores, proxy fence, arrive
+    final_ld=300,      # one 32-column slice of the last layer (ld + dot product)
+    gather_slice=1700, # front end: 4-tap gather of 64 points x 64 channels
+    x2_stage=400, points=500,
+    jitter=0.25,
+)
 
 
 def acc_cols(layer, q):
@@ -34,25 +58,24 @@ def acc_cols(layer, q):
 class Bar:
     def __init__(self, name, count):
         self.name, self.count, self.pending, self.phase = name, count, count, 0
-
-    def arrive(self):
-        self.pending -= 1
-        assert self.pending >= 0, "too many arrivals on " + self.name
-        if self.pending == 0:
-            self.phase += 1
-            self.pending = self.count
+        self.waiters = []
 
     def parity_done(self, parity):          # mbarrier.try_wait.parity semantics
         return (self.phase & 1) != parity
 
 
 class Sim:
-    def __init__(self, tiles, seed, mutate=None):
+    def __init__(self, tiles, seed, mutate=None, params=None):
         self.mutate = mutate
+        self.P = dict(PARAMS)
+        if params:
+            self.P.update(params)
         self.rng = random.Random(seed)
         self.t, self.q, self.n, self.progress_t = 0, [], 0, 0
         self.T, self.S = tiles, 2 * tiles
         self.mma_tail = 0                   # completion time of the last MMA in the tensor-pipe FIFO
+        self.mma_busy = 0
+        NW, NX, NG = self.P["NW"], self.P["NX"], self.P["NG"]
         B = Bar
         self.wfull = [B("wfull%d" % i, 1) for i in range(NW)]      # {expect_tx arrival + bytes}: one event here
         self.wempty = [B("wempty%d" % i, 1) for i in range(NW)]
@@ -64,40 +87,58 @@ class Sim:
         self.acc_full = [[B("acc%d_%d" % (l, nb), 1) for nb in range(2)] for l in range(4)]
         self.acc5_free = B("acc5_free", 2)                          # both epilogue groups
         self.w_slot, self.x_slot, self.x2_slot, self.g_slot = [None] * NW, [None] * NX, None, [None] * NG
-        self.live = []                       # accumulators with undrained slices: [cols, remaining, tag]
+        self.live = []                       # accumulator N-blocks with undrained slices: [cols, remaining, tag]
         self.blocked = {}
+        self.stats = {}                      # (agent, barrier class) -> blocked cycles
 
     # ---- event loop -------------------------------------------------------------------------------
-    def lat(self, lo, hi):
-        return self.rng.randint(lo, hi)
+    def d(self, key, scale=1.0):
+        v = self.P[key] * scale
+        j = self.P["jitter"]
+        return max(1, int(v * self.rng.uniform(1 - j, 1 + j)))
 
     def at(self, dt, fn):
         self.n += 1
         heapq.heappush(self.q, (self.t + dt, self.n, fn))
 
+    def arrive(self, bar):
+        bar.pending -= 1
+        assert bar.pending >= 0, "too many arrivals on " + bar.name
+        if bar.pending == 0:
+            bar.phase += 1
+            bar.pending = bar.count
+            ws, bar.waiters = bar.waiters, []
+            for w in ws:
+                w()
+
     def spawn(self, name, gen):
         def step(val=None):
+            self.progress_t = self.t
             try:
                 op = gen.send(val)
             except StopIteration:
                 self.blocked.pop(name, None)
                 return
             kind = op[0]
-            self.progress_t = self.t
             if kind == "delay":
                 self.at(op[1], step)
             elif kind == "wait":
                 _, bar, parity, want = op
-                def poll():
+                t0 = self.t
+                cls = bar.name.rstrip("0123456789_")
+
+                def check(first=True):
                     if bar.parity_done(parity):
                         assert bar.phase == want + 1, "%s: wait on %s meant phase %d but the barrier has completed %d" % (
                             name, bar.name, want, bar.phase)
                         self.blocked.pop(name, None)
-                        self.at(self.lat(20, 200), step)
+                        cost = self.d("op") if first else self.d("wake")
+                        self.stats[(name, cls)] = self.stats.get((name, cls), 0) + (self.t - t0) + cost
+                        self.at(cost, step)
                     else:
                         self.blocked[name] = (bar.name, want, bar.phase)
-                        self.at(100, poll)
-                poll()
+                        bar.waiters.append(lambda: check(False))
+                check()
             else:
                 raise ValueError(kind)
         self.blocked[name] = ("start", 0, 0)
@@ -106,53 +147,55 @@ class Sim:
     def run(self):
         while self.q:
             self.t, _, fn = heapq.heappop(self.q)
-            if self.t - self.progress_t > 300_000:      # far beyond any latency in the model: nobody can move
-                raise AssertionError("no progress: " + repr(self.blocked))
             fn()
         assert not self.blocked, "deadlock: " + repr(self.blocked)
 
     # ---- tensor pipe ------------------------------------------------------------------------------
     def issue_mmas(self, dur):
         self.mma_tail = max(self.mma_tail, self.t) + dur
+        self.mma_busy += dur
 
     def commit(self, bar):                   # tcgen05.commit: arrive when everything issued so far has retired
-        self.at(max(0, self.mma_tail - self.t) + self.lat(10, 100), bar.arrive)
+        self.at(max(0, self.mma_tail - self.t) + self.d("op", 0.5), lambda: self.arrive(bar))
 
     # ---- agents -----------------------------------------------------------------------------------
-    def stage_of(self, g):
-        """consumption index -> (stream, layer, slice, nb) in the MMA warp's issue order."""
-        return self.order[g]
-
     def build_order(self):
+        """the MMA warp's issue order == the weight stages' consumption order (streams skewed by one layer)"""
         order = []
+
         def layer(sn, l):
             for t in range(SLICES[l]):
                 for nb in range(NNB[l]):
                     order.append((sn, l, t, nb))
-        layer(0, 0)
+        if self.S:
+            layer(0, 0)
         for sn in range(self.S):
-            layer(sn, 1); layer(sn, 2)
+            layer(sn, 1)
+            layer(sn, 2)
             if sn + 1 < self.S:
                 layer(sn + 1, 0)
             layer(sn, 3)
         self.order = order
 
     def producer(self, pw):
+        NW = self.P["NW"]
         g = pw
         while g < len(self.order):
             use = g // NW
             if self.mutate != "no_wempty_wait":
                 yield ("wait", self.wempty[pw], (use & 1) ^ 1, use - 1)
-            yield ("delay", self.lat(50, 300))
+            yield ("delay", self.d("prod_issue"))
+
             def land(g=g, pw=pw):
                 self.w_slot[pw] = g
-                self.wfull[pw].arrive()
-            self.at(self.lat(600, 2500), land)          # bulk copy + peer relay
-            yield ("wait", self.wfull[pw], use & 1, use)
-            yield ("delay", self.lat(50, 300))
+                self.arrive(self.wfull[pw])
+            self.at(self.d("w_copy") + self.d("w_relay"), land)
+            yield ("wait", self.wfull[pw], use & 1, use)          # relay (peer) / re-arm expect_tx (leader)
+            yield ("delay", self.d("op"))
             g += NW
 
     def mma(self):
+        NW, NX = self.P["NW"], self.P["NX"]
         g = 0
         xseq = 0
         for (sn, l, t, nb) in self.order:
@@ -177,20 +220,24 @@ class Sim:
             st = g % NW
             yield ("wait", self.wfull[st], (g // NW) & 1, g // NW)
             assert self.w_slot[st] == g, "W slot %d holds stage %r, wanted %d" % (st, self.w_slot[st], g)
-            yield ("delay", self.lat(100, 400))
-            self.issue_mmas(512)
+            yield ("delay", self.d("stage_misc") + self.d("mma_issue"))
+            self.issue_mmas(self.P["mma_exec"])
+            ncommit = 1
             self.commit(self.wempty[st])
             if t == SLICES[l] - 1:                       # this N-block (128 columns = 4 drain slices) is final
                 self.commit(self.acc_full[l][nb])
+                ncommit += 1
                 c0 = acc_cols(l, q)[0] + 128 * nb
                 self.at(max(0, self.mma_tail - self.t),
                         lambda c=(c0, c0 + 128), tag="acc of L%d/%d stream %d" % (l, nb, sn): self.live.append([c, 4, tag]))
             if nb == NNB[l] - 1:
+                ncommit += 1
                 if l == 0:
                     self.commit(self.x2empty)
                 else:
                     self.commit(self.xempty[xseq % NX])
                     xseq += 1
+            yield ("delay", ncommit * self.d("commit"))
             g += 1
 
     def drained(self, l, q, t):              # 32-column slice t of the accumulator written by layer l was read
@@ -203,24 +250,30 @@ class Sim:
         raise AssertionError("drain of an accumulator that is not complete: L%d parity %d" % (l, q))
 
     def epilogue(self, eg):
+        NX = self.P["NX"]
         gcount = 0
+
         def drain(sn, l_acc, t, seq, gather):
             """read slice t of the accumulator written by layer l_acc, write activation slice `seq`"""
             nonlocal gcount
-            yield ("delay", self.lat(100, 300))          # tcgen05.ld + bias
+            yield ("delay", self.d("drain_pre"))
             if gather:
-                yield ("wait", self.gfull[eg], gcount & 1, gcount)
-                assert self.g_slot[eg] == (sn >> 1) * 8 + t, "gather slot %d holds %r" % (eg, self.g_slot[eg])
-                gcount += 1
+                gs = t % self.P["NG"]
+                yield ("wait", self.gfull[gs], (gcount_of(sn, t) // 1) & 1, gcount_of(sn, t))
+                assert self.g_slot[gs] == (sn >> 1) * 8 + t, "gather slot %d holds %r" % (gs, self.g_slot[gs])
             self.drained(l_acc, sn & 1, t)
             slot = seq % NX
             if self.mutate != "no_xempty_wait":
                 yield ("wait", self.xempty[slot], ((seq // NX) & 1) ^ 1, seq // NX - 1)
-            yield ("delay", self.lat(300, 900))          # convert + store
+            yield ("delay", self.d("drain_post"))
             self.x_slot[slot] = seq
-            self.xfull[slot].arrive()
+            self.arrive(self.xfull[slot])
             if gather:
-                self.gempty[eg].arrive()
+                self.arrive(self.gempty[t % self.P["NG"]])
+
+        def gcount_of(sn, t):                # phase index of the gather slot this slice uses
+            return ((sn >> 1) * 8 + t) // self.P["NG"]
+
         def x3(sn):
             for t in range(eg, 4, 2):
                 if t == eg:
@@ -240,55 +293,86 @@ class Sim:
                 yield from x3(sn + 1)
             yield ("wait", self.acc_full[3][0], sn & 1, sn)
             for t in (2 * eg, 2 * eg + 1):
-                yield ("delay", self.lat(100, 300))
+                yield ("delay", self.d("final_ld"))
                 self.drained(3, sn & 1, t)
-            self.acc5_free.arrive()
+            self.arrive(self.acc5_free)
             if sn + 1 < self.S and self.mutate == "x3_after_final":
                 yield from x3(sn + 1)
 
     def front_end(self):
+        NG = self.P["NG"]
+
         def stage_x2(use):
             yield ("wait", self.x2empty, (use & 1) ^ 1, use - 1)
-            yield ("delay", self.lat(200, 600))
+            yield ("delay", self.d("x2_stage"))
             self.x2_slot = use
-            self.x2full.arrive()
+            self.arrive(self.x2full)
         if self.T:
-            yield ("delay", self.lat(200, 800))          # points of tile 0
+            yield ("delay", self.d("points"))
             yield from stage_x2(0)
         for it in range(self.T):
             yield from stage_x2(2 * it + 1)
             if it + 1 < self.T:
-                yield ("delay", self.lat(200, 800))      # points of the next tile
+                yield ("delay", self.d("points"))
                 yield from stage_x2(2 * it + 2)
             for t in range(8):
                 gsq = it * 8 + t
                 gs = gsq % NG
                 yield ("wait", self.gempty[gs], ((gsq // NG) & 1) ^ 1, gsq // NG - 1)
-                yield ("delay", self.lat(800, 2500))
+                yield ("delay", self.d("gather_slice"))
                 self.g_slot[gs] = gsq
-                self.gfull[gs].arrive()
+                self.arrive(self.gfull[gs])
 
 
-
-def simulate(tiles=3, seed=0, mutate=None):
+def simulate(tiles=3, seed=0, mutate=None, params=None, want_sim=False):
     """mutate: None (the kernel's protocol); 'no_xempty_wait', 'no_wempty_wait', 'no_acc_wait' are deliberately broken variants
     (tests/test_protocol_cpu.py uses them to show that the checks bite); 'x3_after_final' (the un-skewed epilogue order) and
     'no_acc5_wait' are legal-but-slower / redundant-in-this-model variants."""
-    s = Sim(tiles, seed, mutate)
+    s = Sim(tiles, seed, mutate, params)
+    assert s.P["NG"] == 2 or s.P["NG"] % 2 == 0, "gather ring depth must be even (slice parity <-> epilogue group)"
     s.build_order()
-    for pw in range(NW):
+    for pw in range(s.P["NW"]):
         s.spawn("producer%d" % pw, s.producer(pw))
     s.spawn("mma", s.mma())
     for eg in range(2):
         s.spawn("epilogue%d" % eg, s.epilogue(eg))
     s.spawn("front", s.front_end())
     s.run()
-    return s.t
+    return s if want_sim else s.t
+
+
+def report(tiles, schedules, params):
+    tot, busy, stats = 0, 0, {}
+    for seed in range(schedules):
+        s = simulate(tiles, seed, params=params, want_sim=True)
+        tot += s.t
+        busy += s.mma_busy
+        for k, v in s.stats.items():
+            stats[k] = stats.get(k, 0) + v
+    n = tiles * schedules
+    print("cycles/tile %.0f   tensor pipe busy %.0f (%.0f %%)" % (tot / n, busy / n, 100.0 * busy / tot))
+    for (agent, cls), v in sorted(stats.items()):
+        if agent in ("mma", "epilogue0", "front", "producer0"):
+            print("  %-10s blocked on %-9s %7.0f cycles/tile" % (agent, cls, v / n))
 
 
 if __name__ == "__main__":
-    tiles = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-    ts = [simulate(tiles, seed) for seed in range(n)]
-    print("%d schedules x %d tiles: no deadlock, no aliased wait, no ring/TMEM hazard; model time %d..%d cycles/tile"
-          % (n, tiles, min(ts) // tiles, max(ts) // tiles))
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tiles", type=int, default=6)
+    ap.add_argument("--schedules", type=int, default=20)
+    ap.add_argument("--mode", default="f16f8", choices=["f16f8", "bf16x3"])
+    ap.add_argument("--set", action="append", default=[], help="key=value overrides of PARAMS")
+    ap.add_argument("--report", action="store_true")
+    a = ap.parse_args()
+    prm = {}
+    if a.mode == "bf16x3":
+        prm.update(mma_exec=768, mma_issue=168)
+    for kv in a.set:
+        k, v = kv.split("=")
+        prm[k] = type(PARAMS[k])(float(v))
+    if a.report:
+        report(a.tiles, a.schedules, prm)
+    else:
+        ts = [simulate(a.tiles, seed, params=prm) for seed in range(a.schedules)]
+        print("%d schedules x %d tiles: no deadlock, no aliased wait, no ring/TMEM hazard; model time %d..%d cycles/tile"
+              % (a.schedules, a.tiles, min(ts) // a.tiles, max(ts) // a.tiles))
