@@ -611,9 +611,23 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
       // gather of the projected feature map for the local stream's fold2/conv1 epilogue
       const float* pm = job.pmap + (int64_t)b * Hm * Wm * kHidden;
       const int grp = lane >> 3, q = lane & 7;
+      // The gather is latency bound (first touch of every 128-byte tap line misses L1).  In grid mode neighbouring points
+      // share taps, so one slice's lines fit the small L1 next to the 217 KB of shared memory: while slice t is gathered,
+      // slice t+1's lines are prefetched (one lane per line: 16 points x 4 taps x 2 halves per warp).  Hint only.
+      const bool pf = (job.pts == nullptr);
+      auto prefetch_slice = [&](int t) {
+        const int ppt = fw * 16 + (lane >> 1), phh = lane & 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int off = s.tap_off[pb][ppt][k];
+          if (off >= 0) tc::prefetch_l1(pm + off + fout(phh, 32 * t));
+        }
+      };
+      if (pf) prefetch_slice(0);
       for (int t = 0; t < 8; ++t) {
         const uint32_t gsq = (uint32_t)it * 8 + t;
         const int gs = gsq % NG;
+        if (pf && t + 1 < 8) prefetch_slice(t + 1);
         tc::mbar_wait(&s.gempty[gs], ((gsq / NG) & 1) ^ 1);
         float* gdst = s.g[gs];
 #pragma unroll
