@@ -30,3 +30,11 @@ def test_broken_protocols_are_detected(mutation):
         except AssertionError:
             caught += 1
     assert caught == 10, (mutation, caught)
+
+
+def test_dual_issuer_variant_is_sound():
+    """The protocol of profiles/r01f_experiment_dual_issuer.diff (one MMA warp per N-block, producers owning fixed slots,
+    every waiter observing every phase) -- the variant the round-2 plan builds on -- with 3 and 4 weight slots."""
+    for nw in (3, 4):
+        for seed in range(15):
+            sim.simulate(3, seed, params={"issuers": 2, "NW": nw})

@@ -31,6 +31,8 @@ XS = 20                                     # ring slices per stream (X3: 4, X4:
 
 PARAMS = dict(
     NW=3, NX=3, NG=2,
+    issuers=1,         # 2 = the dual-issuer experiment (profiles/r01f_experiment_dual_issuer.diff): one MMA warp per N-block,
+                       #     producers with fixed slot ownership that do not wait for the data, peer relay warp
     op=100,            # an mbarrier try_wait that succeeds at once / an arrive, on a busy SM
     commit=150,        # tcgen05.commit
     wake=150,          # arrival -> blocked waiter running again (poll + wake-up), incl. the remote arrive of the peer CTA
@@ -80,7 +82,7 @@ class Sim:
         self.wfull = [B("wfull%d" % i, 1) for i in range(NW)]      # {expect_tx arrival + bytes}: one event here
         self.wempty = [B("wempty%d" % i, 1) for i in range(NW)]
         self.xfull = [B("xfull%d" % i, 1) for i in range(NX)]       # per group-slice (4 warps x 2 CTAs in hardware)
-        self.xempty = [B("xempty%d" % i, 1) for i in range(NX)]
+        self.xempty = [B("xempty%d" % i, self.P["issuers"]) for i in range(NX)]
         self.x2full, self.x2empty = B("x2full", 1), B("x2empty", 1)
         self.gfull = [B("gfull%d" % i, 1) for i in range(NG)]
         self.gempty = [B("gempty%d" % i, 1) for i in range(NG)]
@@ -194,13 +196,46 @@ class Sim:
             yield ("delay", self.d("op"))
             g += NW
 
-    def mma(self):
+    def producer_owned(self, slots):
+        """dual-issuer variant: this warp owns `slots` (every phase of their barriers is observed by it alone) and never
+        waits for the data; arrival is observed by the issuers (leader) / relayed by the peer's warp 1"""
+        NW = self.P["NW"]
+        for g in range(len(self.order)):
+            slot = g % NW
+            if slot not in slots:
+                continue
+            use = g // NW
+            yield ("wait", self.wempty[slot], (use & 1) ^ 1, use - 1)
+            yield ("delay", self.d("prod_issue") + self.d("op"))
+
+            def land(g=g, slot=slot):
+                self.w_slot[slot] = g
+                self.arrive(self.wfull[slot])
+            self.at(self.d("w_copy") + self.d("w_relay"), land)
+
+    def mma(self, which=0):
         NW, NX = self.P["NW"], self.P["NX"]
+        dual = self.P["issuers"] == 2
         g = 0
         xseq = 0
         for (sn, l, t, nb) in self.order:
             q = sn & 1
-            if t == 0 and nb == 0:
+            mine = (not dual) or (nb == which if NNB[l] == 2 else which == 0)
+            if dual and not mine:                        # the other issuer's stage
+                if nb == 0 and l != 0:                   # still observe the activation slice (keeps the two in step)
+                    slot = xseq % NX
+                    yield ("wait", self.xfull[slot], (xseq // NX) & 1, xseq // NX)
+                if t == 0 and nb == 0 and l == 2 and sn > 0:
+                    yield ("wait", self.acc5_free, (sn - 1) & 1, sn - 1)
+                yield ("wait", self.wfull[g % NW], (g // NW) & 1, g // NW)   # observe every phase of the slot
+                if NNB[l] == 1 and l != 0:               # nothing to issue on this slice: release it right away
+                    self.arrive(self.xempty[xseq % NX])
+                    yield ("delay", self.d("commit"))
+                if nb == NNB[l] - 1 and l != 0:
+                    xseq += 1
+                g += 1
+                continue
+            if t == 0 and nb == (which if (dual and NNB[l] == 2) else 0):
                 if l == 2 and sn > 0 and self.mutate != "no_acc5_wait":
                     yield ("wait", self.acc5_free, (sn - 1) & 1, sn - 1)
                 cols = acc_cols(l, q)
@@ -208,7 +243,7 @@ class Sim:
                     assert rem == 0 or c[1] <= cols[0] or cols[1] <= c[0], \
                         "L%d of stream %d overwrites %s with %d undrained slices" % (l, sn, tag, rem)
                 self.live = [e for e in self.live if e[1] > 0]
-            if nb == 0:                                  # activation slice
+            if nb == 0 or (dual and which == 1):         # activation slice (first stage of the slice for this issuer)
                 if l == 0:
                     yield ("wait", self.x2full, sn & 1, sn)
                     assert self.x2_slot == sn, "X2 slot holds stream %r, wanted %d" % (self.x2_slot, sn)
@@ -230,13 +265,14 @@ class Sim:
                 c0 = acc_cols(l, q)[0] + 128 * nb
                 self.at(max(0, self.mma_tail - self.t),
                         lambda c=(c0, c0 + 128), tag="acc of L%d/%d stream %d" % (l, nb, sn): self.live.append([c, 4, tag]))
-            if nb == NNB[l] - 1:
+            if nb == NNB[l] - 1 or dual:                 # dual: each issuer releases the slice after its own stage
                 ncommit += 1
                 if l == 0:
                     self.commit(self.x2empty)
                 else:
                     self.commit(self.xempty[xseq % NX])
-                    xseq += 1
+            if nb == NNB[l] - 1 and l != 0:
+                xseq += 1
             yield ("delay", ncommit * self.d("commit"))
             g += 1
 
@@ -331,9 +367,16 @@ def simulate(tiles=3, seed=0, mutate=None, params=None, want_sim=False):
     s = Sim(tiles, seed, mutate, params)
     assert s.P["NG"] == 2 or s.P["NG"] % 2 == 0, "gather ring depth must be even (slice parity <-> epilogue group)"
     s.build_order()
-    for pw in range(s.P["NW"]):
-        s.spawn("producer%d" % pw, s.producer(pw))
-    s.spawn("mma", s.mma())
+    if s.P["issuers"] == 2:
+        assert s.P["NW"] >= 3
+        s.spawn("producer0", s.producer_owned({0}))
+        s.spawn("producer1", s.producer_owned(set(range(1, s.P["NW"]))))
+        s.spawn("mma", s.mma(0))
+        s.spawn("mmaB", s.mma(1))
+    else:
+        for pw in range(s.P["NW"]):
+            s.spawn("producer%d" % pw, s.producer(pw))
+        s.spawn("mma", s.mma())
     for eg in range(2):
         s.spawn("epilogue%d" % eg, s.epilogue(eg))
     s.spawn("front", s.front_end())
@@ -357,6 +400,8 @@ def report(tiles, schedules, params):
 
 
 if __name__ == "__main__":
+    import signal
+    signal.signal(signal.SIGPIPE, signal.SIG_DFL)
     ap = argparse.ArgumentParser()
     ap.add_argument("--tiles", type=int, default=6)
     ap.add_argument("--schedules", type=int, default=20)
