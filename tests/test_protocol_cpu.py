@@ -38,3 +38,22 @@ def test_dual_issuer_variant_is_sound():
     for nw in (3, 4):
         for seed in range(15):
             sim.simulate(3, seed, params={"issuers": 2, "NW": nw})
+
+
+def test_protocols_survive_heavy_jitter():
+    for prm in ({}, {"issuers": 2}, {"issuers": 2, "NW": 4}):
+        for seed in range(12):
+            sim.simulate(6, seed, params=dict(prm, jitter=0.9))
+
+
+def test_issuer_that_skips_phases_aliases():
+    """The bug of the first dual-issuer attempt: an issuer that waits only for its own stages sees a stale parity once the
+    two issuers drift apart (needs strongly varying latencies to show up -- as it needed 1792 tiles x 74 pairs on the GPU)."""
+    caught = 0
+    for seed in range(20):
+        try:
+            sim.simulate(10, seed, "dual_skip_phases", {"issuers": 2, "jitter": 0.9})
+        except AssertionError as e:
+            assert "meant phase" in str(e) or "holds stage" in str(e) or "no progress" in str(e) or "deadlock" in str(e)
+            caught += 1
+    assert caught >= 5, caught

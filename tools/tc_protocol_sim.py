@@ -227,7 +227,8 @@ class Sim:
                     yield ("wait", self.xfull[slot], (xseq // NX) & 1, xseq // NX)
                 if t == 0 and nb == 0 and l == 2 and sn > 0:
                     yield ("wait", self.acc5_free, (sn - 1) & 1, sn - 1)
-                yield ("wait", self.wfull[g % NW], (g // NW) & 1, g // NW)   # observe every phase of the slot
+                if self.mutate != "dual_skip_phases":
+                    yield ("wait", self.wfull[g % NW], (g // NW) & 1, g // NW)   # observe every phase of the slot
                 if NNB[l] == 1 and l != 0:               # nothing to issue on this slice: release it right away
                     self.arrive(self.xempty[xseq % NX])
                     yield ("delay", self.d("commit"))
@@ -362,7 +363,8 @@ class Sim:
 
 def simulate(tiles=3, seed=0, mutate=None, params=None, want_sim=False):
     """mutate: None (the kernel's protocol); 'no_xempty_wait', 'no_wempty_wait', 'no_acc_wait' are deliberately broken variants
-    (tests/test_protocol_cpu.py uses them to show that the checks bite); 'x3_after_final' (the un-skewed epilogue order) and
+    (tests/test_protocol_cpu.py uses them to show that the checks bite), and 'dual_skip_phases' (issuers=2 where an issuer only
+    waits for its own stages -- the aliasing bug of the first dual-issuer attempt); 'x3_after_final' (the un-skewed epilogue order) and
     'no_acc5_wait' are legal-but-slower / redundant-in-this-model variants."""
     s = Sim(tiles, seed, mutate, params)
     assert s.P["NG"] == 2 or s.P["NG"] % 2 == 0, "gather ring depth must be even (slice parity <-> epilogue group)"
