@@ -35,15 +35,29 @@ def test_broken_protocols_are_detected(mutation):
 def test_dual_issuer_variant_is_sound():
     """The protocol of profiles/r01f_experiment_dual_issuer.diff (one MMA warp per N-block, producers owning fixed slots,
     every waiter observing every phase) -- the variant the round-2 plan builds on -- with 3 and 4 weight slots."""
-    for nw in (3, 4):
+    for prm in ({"issuers": 2, "NW": 3}, {"issuers": 2, "NW": 4, "split_wfull": 1}):
         for seed in range(15):
-            sim.simulate(3, seed, params={"issuers": 2, "NW": nw})
+            sim.simulate(3, seed, params=prm)
 
 
 def test_protocols_survive_heavy_jitter():
-    for prm in ({}, {"issuers": 2}, {"issuers": 2, "NW": 4}):
+    """shipped protocol, the dual-issuer experiment (3 slots), and the round-2 candidate: two issuers with one "stage landed"
+    barrier per (issuer, slot) and 4 weight slots"""
+    for prm in ({}, {"issuers": 2}, {"issuers": 2, "NW": 4, "split_wfull": 1}, {"issuers": 2, "NW": 3, "split_wfull": 1}):
         for seed in range(12):
             sim.simulate(6, seed, params=dict(prm, jitter=0.9))
+
+
+def test_observe_all_dual_issuer_with_four_slots_is_unsound():
+    """Found by the model, not on the GPU: with 4 slots an issuer that merely *observes* the other's stages can fall two
+    phases behind a slot's barrier -> the per-issuer barriers above are required."""
+    bad = 0
+    for seed in range(40):
+        try:
+            sim.simulate(8, seed, params={"issuers": 2, "NW": 4, "jitter": 0.9})
+        except AssertionError:
+            bad += 1
+    assert bad >= 1
 
 
 def test_issuer_that_skips_phases_aliases():

@@ -31,6 +31,8 @@ XS = 20                                     # ring slices per stream (X3: 4, X4:
 
 PARAMS = dict(
     NW=3, NX=3, NG=2,
+    split_wfull=0,     # issuers=2 only: 1 = one 'stage landed' barrier per (issuer, slot), signalled according to the static
+                       #     stage -> issuer map, so that an issuer only ever waits on barriers whose every phase is its own
     issuers=1,         # 2 = the dual-issuer experiment (profiles/r01f_experiment_dual_issuer.diff): one MMA warp per N-block,
                        #     producers with fixed slot ownership that do not wait for the data, peer relay warp
     op=100,            # an mbarrier try_wait that succeeds at once / an arrive, on a busy SM
@@ -81,6 +83,8 @@ class Sim:
         B = Bar
         self.wfull = [B("wfull%d" % i, 1) for i in range(NW)]      # {expect_tx arrival + bytes}: one event here
         self.wempty = [B("wempty%d" % i, 1) for i in range(NW)]
+        self.wfull_i = [[B("wfull%c%d" % ("AB"[w], i), 1) for i in range(NW)] for w in range(2)]
+        self.wuse = [[0] * NW for _ in range(2)]      # per issuer: uses of each slot so far
         self.xfull = [B("xfull%d" % i, 1) for i in range(NX)]       # per group-slice (4 warps x 2 CTAs in hardware)
         self.xempty = [B("xempty%d" % i, self.P["issuers"]) for i in range(NX)]
         self.x2full, self.x2empty = B("x2full", 1), B("x2empty", 1)
@@ -210,7 +214,11 @@ class Sim:
 
             def land(g=g, slot=slot):
                 self.w_slot[slot] = g
-                self.arrive(self.wfull[slot])
+                if self.P["split_wfull"]:
+                    sn_, l_, t_, nb_ = self.order[g]
+                    self.arrive(self.wfull_i[nb_ if NNB[l_] == 2 else 0][slot])
+                else:
+                    self.arrive(self.wfull[slot])
             self.at(self.d("w_copy") + self.d("w_relay"), land)
 
     def mma(self, which=0):
@@ -227,7 +235,7 @@ class Sim:
                     yield ("wait", self.xfull[slot], (xseq // NX) & 1, xseq // NX)
                 if t == 0 and nb == 0 and l == 2 and sn > 0:
                     yield ("wait", self.acc5_free, (sn - 1) & 1, sn - 1)
-                if self.mutate != "dual_skip_phases":
+                if self.mutate != "dual_skip_phases" and not self.P["split_wfull"]:
                     yield ("wait", self.wfull[g % NW], (g // NW) & 1, g // NW)   # observe every phase of the slot
                 if NNB[l] == 1 and l != 0:               # nothing to issue on this slice: release it right away
                     self.arrive(self.xempty[xseq % NX])
@@ -254,7 +262,12 @@ class Sim:
                     want = sn * XS + {1: 0, 2: 4, 3: 12}[l] + t
                     assert self.x_slot[slot] == want, "X slot %d holds %r, wanted %d" % (slot, self.x_slot[slot], want)
             st = g % NW
-            yield ("wait", self.wfull[st], (g // NW) & 1, g // NW)
+            if dual and self.P["split_wfull"]:
+                u = self.wuse[which][st]
+                self.wuse[which][st] += 1
+                yield ("wait", self.wfull_i[which][st], u & 1, u)
+            else:
+                yield ("wait", self.wfull[st], (g // NW) & 1, g // NW)
             assert self.w_slot[st] == g, "W slot %d holds stage %r, wanted %d" % (st, self.w_slot[st], g)
             yield ("delay", self.d("stage_misc") + self.d("mma_issue"))
             self.issue_mmas(self.P["mma_exec"])
