@@ -71,3 +71,21 @@ def test_issuer_that_skips_phases_aliases():
             assert "meant phase" in str(e) or "holds stage" in str(e) or "no progress" in str(e) or "deadlock" in str(e)
             caught += 1
     assert caught >= 5, caught
+
+
+ROUND2 = {"x2_in_ring": 1, "NW": 4, "issuers": 2, "split_wfull": 1}
+
+
+@pytest.mark.parametrize("tiles", [1, 2, 7])
+def test_round2_candidate_protocol_is_sound(tiles):
+    """fold1/conv1 output through the activation ring (frees its 16 KB slot), 4 weight slots, two issuers with per-issuer
+    'stage landed' barriers -- the protocol DESIGN.md proposes for the next kernel revision."""
+    for seed in range(15):
+        sim.simulate(tiles, seed, params=ROUND2)
+        sim.simulate(tiles, seed, params=dict(ROUND2, jitter=0.9))
+
+
+def test_round2_candidate_is_faster_in_the_model():
+    base = sum(sim.simulate(6, s) for s in range(5))
+    cand = sum(sim.simulate(6, s, params=ROUND2) for s in range(5))
+    assert cand < 0.93 * base, (cand, base)

@@ -31,6 +31,8 @@ XS = 20                                     # ring slices per stream (X3: 4, X4:
 
 PARAMS = dict(
     NW=3, NX=3, NG=2,
+    x2_in_ring=0,      # 1 = fold1/conv1's output goes through the activation ring (staged by epilogue group 0 from the points
+                       #     the front end publishes), freeing the dedicated 16 KB slot for a fourth weight stage
     split_wfull=0,     # issuers=2 only: 1 = one 'stage landed' barrier per (issuer, slot), signalled according to the static
                        #     stage -> issuer map, so that an issuer only ever waits on barriers whose every phase is its own
     issuers=1,         # 2 = the dual-issuer experiment (profiles/r01f_experiment_dual_issuer.diff): one MMA warp per N-block,
@@ -88,6 +90,8 @@ class Sim:
         self.xfull = [B("xfull%d" % i, 1) for i in range(NX)]       # per group-slice (4 warps x 2 CTAs in hardware)
         self.xempty = [B("xempty%d" % i, self.P["issuers"]) for i in range(NX)]
         self.x2full, self.x2empty = B("x2full", 1), B("x2empty", 1)
+        self.pfull = [B("pfull%d" % i, 1) for i in range(2)]          # points of tile parity i published by the front end
+        self.points = [None, None]
         self.gfull = [B("gfull%d" % i, 1) for i in range(NG)]
         self.gempty = [B("gempty%d" % i, 1) for i in range(NG)]
         self.acc_full = [[B("acc%d_%d" % (l, nb), 1) for nb in range(2)] for l in range(4)]
@@ -165,6 +169,18 @@ class Sim:
         self.at(max(0, self.mma_tail - self.t) + self.d("op", 0.5), lambda: self.arrive(bar))
 
     # ---- agents -----------------------------------------------------------------------------------
+    def seq_of(self, sn, kind, t=0):
+        """index of an activation slice in the ring's production/consumption order; kind: 2 (fold1/conv1 output of stream sn,
+        only with x2_in_ring), 3, 4, 5 (outputs of tensor-core layers L0, L1, L2 of stream sn)"""
+        if not self.P["x2_in_ring"]:
+            return sn * XS + {3: 0, 4: 4, 5: 12}[kind] + t
+        if kind == 2:
+            return 0 if sn == 0 else 1 + 21 * (sn - 1) + 12
+        base = 1 + 21 * sn
+        if kind == 5:
+            return base + 12 + (1 if sn + 1 < self.S else 0) + t
+        return base + {3: 0, 4: 4}[kind] + t
+
     def build_order(self):
         """the MMA warp's issue order == the weight stages' consumption order (streams skewed by one layer)"""
         order = []
@@ -230,17 +246,18 @@ class Sim:
             q = sn & 1
             mine = (not dual) or (nb == which if NNB[l] == 2 else which == 0)
             if dual and not mine:                        # the other issuer's stage
-                if nb == 0 and l != 0:                   # still observe the activation slice (keeps the two in step)
+                ring = l != 0 or self.P["x2_in_ring"]
+                if nb == 0 and ring:                     # still observe the activation slice (keeps the two in step)
                     slot = xseq % NX
                     yield ("wait", self.xfull[slot], (xseq // NX) & 1, xseq // NX)
                 if t == 0 and nb == 0 and l == 2 and sn > 0:
                     yield ("wait", self.acc5_free, (sn - 1) & 1, sn - 1)
                 if self.mutate != "dual_skip_phases" and not self.P["split_wfull"]:
                     yield ("wait", self.wfull[g % NW], (g // NW) & 1, g // NW)   # observe every phase of the slot
-                if NNB[l] == 1 and l != 0:               # nothing to issue on this slice: release it right away
+                if NNB[l] == 1 and ring:                 # nothing to issue on this slice: release it right away
                     self.arrive(self.xempty[xseq % NX])
                     yield ("delay", self.d("commit"))
-                if nb == NNB[l] - 1 and l != 0:
+                if nb == NNB[l] - 1 and ring:
                     xseq += 1
                 g += 1
                 continue
@@ -253,13 +270,14 @@ class Sim:
                         "L%d of stream %d overwrites %s with %d undrained slices" % (l, sn, tag, rem)
                 self.live = [e for e in self.live if e[1] > 0]
             if nb == 0 or (dual and which == 1):         # activation slice (first stage of the slice for this issuer)
-                if l == 0:
+                if l == 0 and not self.P["x2_in_ring"]:
                     yield ("wait", self.x2full, sn & 1, sn)
                     assert self.x2_slot == sn, "X2 slot holds stream %r, wanted %d" % (self.x2_slot, sn)
                 else:
                     slot = xseq % NX
                     yield ("wait", self.xfull[slot], (xseq // NX) & 1, xseq // NX)
-                    want = sn * XS + {1: 0, 2: 4, 3: 12}[l] + t
+                    want = self.seq_of(sn, 2 + l, t)
+                    assert want == xseq, "ring order: issuer at %d, slice is %d" % (xseq, want)
                     assert self.x_slot[slot] == want, "X slot %d holds %r, wanted %d" % (slot, self.x_slot[slot], want)
             st = g % NW
             if dual and self.P["split_wfull"]:
@@ -281,11 +299,11 @@ class Sim:
                         lambda c=(c0, c0 + 128), tag="acc of L%d/%d stream %d" % (l, nb, sn): self.live.append([c, 4, tag]))
             if nb == NNB[l] - 1 or dual:                 # dual: each issuer releases the slice after its own stage
                 ncommit += 1
-                if l == 0:
+                if l == 0 and not self.P["x2_in_ring"]:
                     self.commit(self.x2empty)
                 else:
                     self.commit(self.xempty[xseq % NX])
-            if nb == NNB[l] - 1 and l != 0:
+            if nb == NNB[l] - 1 and (l != 0 or self.P["x2_in_ring"]):
                 xseq += 1
             yield ("delay", ncommit * self.d("commit"))
             g += 1
@@ -328,8 +346,22 @@ class Sim:
             for t in range(eg, 4, 2):
                 if t == eg:
                     yield ("wait", self.acc_full[0][0], sn & 1, sn)
-                yield from drain(sn, 0, t, sn * XS + t, False)
+                yield from drain(sn, 0, t, self.seq_of(sn, 3, t), False)
+
+        def x2(sn):                          # fold1/conv1 of stream sn from the published points (group 0 only)
+            tile = sn >> 1
+            yield ("wait", self.pfull[tile & 1], (tile >> 1) & 1, tile >> 1)
+            assert self.points[tile & 1] == tile, "points buffer holds tile %r, wanted %d" % (self.points[tile & 1], tile)
+            seq = self.seq_of(sn, 2)
+            slot = seq % NX
+            yield ("wait", self.xempty[slot], ((seq // NX) & 1) ^ 1, seq // NX - 1)
+            yield ("delay", self.d("x2_stage"))
+            self.x_slot[slot] = seq
+            self.arrive(self.xfull[slot])
+        ring2 = self.P["x2_in_ring"] and eg == 0
         if self.S:
+            if ring2:
+                yield from x2(0)
             yield from x3(0)
         for sn in range(self.S):
             for l_acc, off in ((1, 4), (2, 12)):
@@ -338,7 +370,9 @@ class Sim:
                         yield ("wait", self.acc_full[l_acc][0], sn & 1, sn)
                     if t == eg + 4:
                         yield ("wait", self.acc_full[l_acc][1], sn & 1, sn)
-                    yield from drain(sn, l_acc, t, sn * XS + off + t, l_acc == 2 and (sn & 1) == 1)
+                    yield from drain(sn, l_acc, t, self.seq_of(sn, 3 + l_acc, t), l_acc == 2 and (sn & 1) == 1)
+                if l_acc == 1 and ring2 and sn + 1 < self.S:
+                    yield from x2(sn + 1)         # ring order: ... X4_n, X2_{n+1}, X5_n ...
             if sn + 1 < self.S and self.mutate != "x3_after_final":
                 yield from x3(sn + 1)
             yield ("wait", self.acc_full[3][0], sn & 1, sn)
@@ -357,14 +391,25 @@ class Sim:
             yield ("delay", self.d("x2_stage"))
             self.x2_slot = use
             self.arrive(self.x2full)
-        if self.T:
+        def publish(tile):
+            yield ("delay", self.d("points"))
+            self.points[tile & 1] = tile
+            self.arrive(self.pfull[tile & 1])
+        if self.P["x2_in_ring"]:
+            if self.T:
+                yield from publish(0)
+        elif self.T:
             yield ("delay", self.d("points"))
             yield from stage_x2(0)
         for it in range(self.T):
-            yield from stage_x2(2 * it + 1)
-            if it + 1 < self.T:
-                yield ("delay", self.d("points"))
-                yield from stage_x2(2 * it + 2)
+            if self.P["x2_in_ring"]:
+                if it + 1 < self.T:
+                    yield from publish(it + 1)
+            else:
+                yield from stage_x2(2 * it + 1)
+                if it + 1 < self.T:
+                    yield ("delay", self.d("points"))
+                    yield from stage_x2(2 * it + 2)
             for t in range(8):
                 gsq = it * 8 + t
                 gs = gsq % NG
