@@ -118,6 +118,7 @@ struct disn_ctx {
   int64_t tc_weights_bytes = 0;
   void* tc_weights_f8 = nullptr;       // fp16 + e5m2 stage images (DISN_PREC_F16F8)
   float tc_act_scale[2][4][2] = {};
+  float tc_small[2][2048] = {};         // host copy of the per-stream small parameters (experimental v2 kernel's parameter table)
   std::map<std::string, uint8_t*> enc_tc_weights;   // packed bf16 hi/lo stage images of the encoder GEMMs
 };
 
@@ -132,6 +133,7 @@ int launch_point_fp32(disn_ctx* c, const PointJob& job);
 // point_tc.cu
 int tc_pack_weights(disn_ctx* c);
 int launch_point_tc(disn_ctx* c, const PointJob& job);
+int launch_point_tc_v2(disn_ctx* c, const PointJob& job);   // experimental (DISN_TC_V2=1), point_tc_v2.cu
 // conv_tc.cu
 int conv_tc_pack(disn_ctx* c, const float* d_w, int K, int N, uint8_t** out_dev);
 int launch_conv_tc(disn_ctx* c, const float* A, const uint8_t* wpk, const float* bias, float* C, float* ws,

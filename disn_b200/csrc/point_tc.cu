@@ -693,6 +693,22 @@ int tc_pack_weights(disn_ctx* c) {
   }
   DISN_CUDA_OK(cudaMemcpyAsync(c->tc_weights_f8, img.data(), total, cudaMemcpyHostToDevice, c->stream));
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+
+  // host copy of the small per-stream parameters at the SB_* offsets (parameter table of the experimental v2 kernel)
+  for (int sidx = 0; sidx < 2; ++sidx) {
+    const std::string p = sidx ? "sdfprediction_imgfeat" : "sdfprediction";
+    const struct { const char* name; int off, n; } small[7] = {
+        {"/fold1/conv2/biases", SB_B2, 256}, {"/fold1/conv3/biases", SB_B3, 512}, {"/fold2/conv1/biases", SB_B4, 512},
+        {"/fold2/conv2/biases", SB_B5, 256}, {"/fold2/conv5/weights", SB_W6, 256}, {"/fold1/conv1/weights", SB_W1, 192},
+        {"/fold1/conv1/biases", SB_B1, 64}};
+    for (const auto& e : small) {
+      auto it = c->weights.find(p + e.name);
+      DISN_REQUIRE(it != c->weights.end() && it->second.numel == e.n, "missing or mis-shaped variable " + p + e.name);
+      DISN_CUDA_OK(cudaMemcpyAsync(&c->tc_small[sidx][e.off], it->second.ptr, (size_t)e.n * sizeof(float),
+                                   cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -711,6 +727,9 @@ static int launch_variant(disn_ctx* c, const PointJob& job, const void* wpk, int
 }
 
 int launch_point_tc(disn_ctx* c, const PointJob& job_in) {
+  if (const char* v2 = getenv("DISN_TC_V2")) {      // experimental kernel revision, see point_tc_v2.cu
+    if (v2[0] == '1') return launch_point_tc_v2(c, job_in);
+  }
   const bool f8 = c->cfg.precision == DISN_PREC_F16F8;
   const void* wpk = f8 ? c->tc_weights_f8 : c->tc_weights;
   DISN_REQUIRE(wpk != nullptr, "tensor-core weights not packed (call disn_finalize_weights)");

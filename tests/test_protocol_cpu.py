@@ -89,3 +89,48 @@ def test_round2_candidate_is_faster_in_the_model():
     base = sum(sim.simulate(6, s) for s in range(5))
     cand = sum(sim.simulate(6, s, params=ROUND2) for s in range(5))
     assert cand < 0.93 * base, (cand, base)
+
+
+def test_v2_static_maps_agree_with_the_issue_order():
+    """point_tc_v2.cu's stage_info() (stage -> image position, consuming issuer) and ring_seq() (activation slice -> ring
+    position), restated here, against the MMA issue order and tc_pack_weights' kCyclePos -- incl. the last tile, which has no
+    'next stream' entry."""
+    FIRST_L0_POS, SPS = 57, 33
+    kCyclePos = [[FIRST_L0_POS, 0, 8, 25], [24, 33, 41, 58]]
+    SL, NNB = {0: 1, 1: 4, 2: 8, 3: 8}, {0: 1, 1: 2, 2: 2, 3: 1}
+
+    def stage_info(g, tiles):
+        if g == 0:
+            return FIRST_L0_POS, 0
+        cidx, last0 = g - 1, (tiles - 1) * 2 * SPS
+        r = cidx % (2 * SPS)
+        if cidx >= last0 and cidx - last0 >= FIRST_L0_POS:
+            r = cidx - last0 + 1
+        issuer = (r & 1) if r < 24 else (((r - 33) & 1) if 33 <= r < 57 else 0)
+        return r, issuer
+
+    for tiles in (1, 2, 3, 6):
+        S = 2 * tiles
+
+        def ring_seq(sn, kind, t):
+            if kind == 2:
+                return 0 if sn == 0 else 1 + 21 * (sn - 1) + 12
+            base = 1 + 21 * sn
+            return base + 12 + (1 if sn + 1 < S else 0) + t if kind == 5 else base + (0 if kind == 3 else 4) + t
+
+        g = x = 0
+        for grp in range(-1, S):
+            for q in range(4):
+                layer = (1, 2, 0, 3)[q]
+                sn = grp + 1 if q == 2 else grp
+                if sn < 0 or sn >= S:
+                    continue
+                for t in range(SL[layer]):
+                    assert ring_seq(sn, 2 + layer, t) == x
+                    x += 1
+                    for nb in range(NNB[layer]):
+                        img, issuer = stage_info(g, tiles)
+                        assert img == kCyclePos[sn & 1][layer] + t * NNB[layer] + nb
+                        assert issuer == (nb if NNB[layer] == 2 else 0)
+                        g += 1
+        assert g == 66 * tiles
