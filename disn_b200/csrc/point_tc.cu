@@ -695,6 +695,7 @@ int tc_pack_weights(disn_ctx* c) {
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
 
   // host copy of the small per-stream parameters at the SB_* offsets (parameter table of the experimental v2 kernel)
+  c->tc_small_ok = true;
   for (int sidx = 0; sidx < 2; ++sidx) {
     const std::string p = sidx ? "sdfprediction_imgfeat" : "sdfprediction";
     const struct { const char* name; int off, n; } small[7] = {
@@ -703,7 +704,10 @@ int tc_pack_weights(disn_ctx* c) {
         {"/fold1/conv1/biases", SB_B1, 64}};
     for (const auto& e : small) {
       auto it = c->weights.find(p + e.name);
-      DISN_REQUIRE(it != c->weights.end() && it->second.numel == e.n, "missing or mis-shaped variable " + p + e.name);
+      if (it == c->weights.end() || it->second.numel != e.n) {   // never fatal here: only the experimental kernel needs it
+        c->tc_small_ok = false;
+        continue;
+      }
       DISN_CUDA_OK(cudaMemcpyAsync(&c->tc_small[sidx][e.off], it->second.ptr, (size_t)e.n * sizeof(float),
                                    cudaMemcpyDeviceToHost, c->stream));
     }

@@ -522,6 +522,7 @@ int launch_point_tc_v2(disn_ctx* c, const PointJob& job_in) {
   const bool f8 = c->cfg.precision == DISN_PREC_F16F8;
   const void* wpk = f8 ? c->tc_weights_f8 : c->tc_weights;
   DISN_REQUIRE(wpk != nullptr, "tensor-core weights not packed (call disn_finalize_weights)");
+  DISN_REQUIRE(c->tc_small_ok, "small-parameter table was not built (unexpected variable shapes)");
   static_assert(sizeof(SmallParams) == sizeof(c->tc_small), "small-parameter table layout");
   PointJob job = job_in;
   memcpy(job.act_scale, c->tc_act_scale, sizeof(job.act_scale));
