@@ -139,3 +139,23 @@ def test_tf_checkpoint_bundle_round_trip(tmp_path):
     with pytest.raises(ValueError, match="bad table magic"):
         open(prefix + ".bad.index", "wb").write(b"x" * 100)
         ck.read_index(prefix + ".bad.index")
+
+
+def test_demo_image_loader_and_gt_camera(tmp_path):
+    """demo/demo.py:261-279: PNG -> [1,137,137,3] float32 in [0,1] (alpha dropped), the hard-coded GT trans_mat and
+    sdf_params = [-1,-1,-1,1,1,1]."""
+    import cv2
+    from disn_b200 import create_sdf as drv
+    from disn_b200 import demo, synth
+    drv.configure(demo.default_flags(log_dir=str(tmp_path)))
+    img = (np.random.default_rng(0).random((137, 137, 4)) * 255).astype(np.uint8)
+    path = str(tmp_path / "render.png")
+    cv2.imwrite(path, img)
+    bd = demo.read_img_get_transmat(path)
+    np.testing.assert_array_equal(bd["img"][0], img[:, :, :3].astype(np.float32) / 255.)
+    np.testing.assert_array_equal(bd["trans_mat"], synth.DEMO_TRANS_MAT)
+    np.testing.assert_array_equal(bd["sdf_params"], [[-1, -1, -1, 1, 1, 1]])
+    with pytest.raises(FileNotFoundError):
+        demo.read_img_get_transmat(str(tmp_path / "missing.png"))
+    with pytest.raises(RuntimeError):           # --cam_est without the camera checkpoint's variables
+        demo.read_img_get_transmat(path, cam_est=True)
