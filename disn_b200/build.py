@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdisn_b200.so")
-SOURCES = ["api.cu", "encoder.cu", "point_fp32.cu", "point_tc.cu", "tc_selftest.cu", "tc_probe.cu", "mc.cu", "chamfer.cu", "conv_tc.cu", "cam.cu", "point_tc_v2.cu"]
+SOURCES = ["api.cu", "encoder.cu", "point_fp32.cu", "point_tc.cu", "tc_selftest.cu", "tc_probe.cu", "mc.cu", "chamfer.cu", "conv_tc.cu", "cam.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-ffp-contract=off", "--expt-relaxed-constexpr", "-shared"]

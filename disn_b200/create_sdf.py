@@ -39,7 +39,7 @@ def default_flags(**kw):
     d = dict(gpu="0", img_h=137, img_w=137, batch_size=1, num_classes=1024, num_points=1, sdf_res=64, alpha=False,
              rot=False, tanh=False, multi_view=False, num_sample_points=1, log_dir="checkpoint/SDF_DISN",
              iso=0.0, threedcnn=False, img_feat_onestream=False, img_feat_twostream=True, binary=False,
-             cam_est=False, view_num=24, category="all", precision="bf16x3")
+             cam_est=False, view_num=24, category="all", precision="f16f8")
     d.update(kw)
     return SimpleNamespace(**d)
 
@@ -88,7 +88,7 @@ def create(weights, batches, device=0):
     is_training_pl = model.Placeholder("is_training", ())
     end_points = model.get_model(input_pls, NUM_POINTS, is_training_pl, bn=False, FLAGS=FLAGS)
     loss, end_points = model.get_loss(end_points, sdf_weight=SDF_WEIGHT, num_sample_points=NUM_SAMPLE_POINTS, FLAGS=FLAGS)
-    sess = model.Session(device=device, precision=getattr(FLAGS, "precision", "bf16x3"), max_batch=max(1, BATCH_SIZE))
+    sess = model.Session(device=device, precision=getattr(FLAGS, "precision", "f16f8"), max_batch=max(1, BATCH_SIZE))
     if weights is None:
         print("Fail to load overall modelfile: %s" % LOG_DIR)       # create_sdf.py:192
         raise RuntimeError("no weights supplied: pass the checkpoint variables (or a random init) explicitly")

@@ -50,9 +50,14 @@ int disn_create(const disn_config* cfg, disn_ctx** out) {
   }
   disn_ctx* c = new disn_ctx();
   c->cfg = *cfg;
+  c->num_sms = prop.multiProcessorCount;
   DISN_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
   DISN_CUDA_OK(cudaMalloc(&c->d_tm, sizeof(float) * 12 * 8));
+  DISN_CUDA_OK(cudaMalloc(&c->d_status, sizeof(int)));
+  DISN_CUDA_OK(cudaMemset(c->d_status, 0, sizeof(int)));
+  DISN_CUDA_OK(cudaMallocHost(&c->h_status, sizeof(int)));
+  *c->h_status = 0;
   *out = c;
   return 0;
 }
@@ -67,8 +72,26 @@ void disn_destroy(disn_ctx* c) {
     if (p) cudaFree(p);
   for (auto& kv : c->enc_tc_weights) cudaFree(kv.second);
   if (c->tc_weights) cudaFree(c->tc_weights);
+  if (c->tc_weights_f8) cudaFree(c->tc_weights_f8);
+  if (c->d_status) cudaFree(c->d_status);
+  if (c->h_status) cudaFreeHost(c->h_status);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+// Call after a synchronisation of c->stream: turns failure bits the kernels raised into a loud error.
+static int check_status(disn_ctx* c) {
+  const int st = *c->h_status;
+  if (st == 0) return 0;
+  *c->h_status = 0;
+  cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
+  if (st & DISN_STATUS_FP16_OVERFLOW) {
+    set_error("DISN_PREC_F16F8: an MLP activation exceeded the fp16 range (65504); the result is invalid -- "
+              "use DISN_PREC_BF16X3 (fp32 range) for these weights");
+    return -4;
+  }
+  set_error("kernel reported status " + std::to_string(st));
+  return -4;
 }
 
 int disn_set_stream(disn_ctx* c, void* cuda_stream) {
@@ -90,7 +113,7 @@ int disn_synchronize(disn_ctx* c) {
   DISN_REQUIRE(c, "null ctx");
   DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_status(c);     // asynchronous (DISN_DEVICE_PTR) launches report here
 }
 
 int disn_set_precision(disn_ctx* c, int32_t precision) {
@@ -120,8 +143,10 @@ int disn_load_weight(disn_ctx* c, const char* name, const float* data, const int
   DISN_CUDA_OK(cudaMemcpyAsync(t.ptr, data, numel * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));   // caller-owned host buffer; ordered on the ctx stream
   c->weights_dirty = true;
+  c->enc_B = 0;     // encoder products (taps, gbias, pmap) belong to the previous weights: force a new disn_encode
   for (auto& kv : c->enc_tc_weights) cudaFree(kv.second);     // packed encoder weights follow the fp32 masters
   c->enc_tc_weights.clear();
+  encoder_graph_reset(c);    // the graph replays launches that read the old packed images
   return 0;
 }
 
@@ -210,6 +235,16 @@ static int ensure_scratch(disn_ctx* c, int64_t pts) {
   return 0;
 }
 
+// Device-visible alias of a caller buffer that is pinned (cudaHostAlloc / cudaHostRegister / torch pin_memory), else
+// nullptr.  With unified addressing the kernel epilogue can store its 4 B per point straight into such memory over PCIe
+// (~1 GB/s at 2.5e8 points/s), so the host result needs no device scratch and no device->host copy after the kernel.
+static float* pinned_alias(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type == cudaMemoryTypeHost && a.devicePointer) return static_cast<float*>(a.devicePointer);
+  return nullptr;
+}
+
 static int run_job(disn_ctx* c, PointJob& job) {
   job.gbias = c->gbias;
   job.pmap = c->pmap;
@@ -218,8 +253,12 @@ static int run_job(disn_ctx* c, PointJob& job) {
   job.tanh_out = c->cfg.tanh_out;
   fill_stream(c, "sdfprediction", job.g);
   fill_stream(c, "sdfprediction_imgfeat", job.l);
-  if (c->cfg.precision != DISN_PREC_FP32) return launch_point_tc(c, job);
-  return launch_point_fp32(c, job);
+  job.status = c->d_status;
+  if (c->cfg.precision == DISN_PREC_FP32) return launch_point_fp32(c, job);
+  if (launch_point_tc(c, job)) return -1;
+  // the status word travels to the pinned mirror behind the kernel; whoever synchronises next checks it
+  DISN_CUDA_OK(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  return 0;
 }
 
 int disn_eval_points(disn_ctx* c, const float* pts, const float* pts_rot, const float* trans_mat, int32_t B,
@@ -231,13 +270,15 @@ int disn_eval_points(disn_ctx* c, const float* pts, const float* pts_rot, const 
   DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
   if (N == 0) return 0;
   PointJob job{};
-  job.B = B; job.N = N; job.out_scale = 1.0f;
+  job.B = B; job.N = N; job.out_div = 1.0f;
   if (flags & DISN_DEVICE_PTR) {
     job.pts = pts; job.pts_rot = (pts_rot && pts_rot != pts) ? pts_rot : nullptr;
     job.trans_mat = trans_mat; job.out_pred = out_pred; job.out_uv = out_uv;
     return run_job(c, job);
   }
   if (ensure_scratch(c, (int64_t)B * N)) return -1;
+  float* pred_alias = pinned_alias(out_pred);
+  float* uv_alias = out_uv ? pinned_alias(out_uv) : nullptr;
   size_t nb = (size_t)B * N * 3 * sizeof(float);
   DISN_CUDA_OK(cudaMemcpyAsync(c->d_pts, pts, nb, cudaMemcpyHostToDevice, c->stream));
   job.pts = c->d_pts;
@@ -247,14 +288,15 @@ int disn_eval_points(disn_ctx* c, const float* pts, const float* pts_rot, const 
   }
   DISN_CUDA_OK(cudaMemcpyAsync(c->d_tm, trans_mat, (size_t)B * 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   job.trans_mat = c->d_tm;
-  job.out_pred = c->d_out;
-  job.out_uv = out_uv ? c->d_uv : nullptr;
+  job.out_pred = pred_alias ? pred_alias : c->d_out;
+  job.out_uv = out_uv ? (uv_alias ? uv_alias : c->d_uv) : nullptr;
   if (run_job(c, job)) return -1;
-  DISN_CUDA_OK(cudaMemcpyAsync(out_pred, c->d_out, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  if (out_uv)
+  if (!pred_alias)
+    DISN_CUDA_OK(cudaMemcpyAsync(out_pred, c->d_out, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (out_uv && !uv_alias)
     DISN_CUDA_OK(cudaMemcpyAsync(out_uv, c->d_uv, (size_t)B * N * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_status(c);
 }
 
 // numpy.linspace(start, stop, num) in float64, then cast to float32 (test/create_sdf.py:247-254):
@@ -305,20 +347,26 @@ int disn_eval_grid(disn_ctx* c, const double* sdf_params, const float* trans_mat
 
   PointJob job{};
   job.B = B; job.N = N; job.R = R; job.z0 = z0; job.axes = c->d_axes;
-  job.out_scale = 1.0f / c->cfg.sdf_weight;
+  job.out_div = c->cfg.sdf_weight;   // correctly rounded r / 10 like the reference's float64 divide + float32 pack (create_sdf.py:285,299)
   if (flags & DISN_DEVICE_PTR) {
     job.trans_mat = trans_mat;
     job.out_pred = out_sdf;
     return run_job(c, job);
   }
-  if (ensure_scratch(c, (int64_t)B * N)) return -1;
   DISN_CUDA_OK(cudaMemcpyAsync(c->d_tm, trans_mat, (size_t)B * 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   job.trans_mat = c->d_tm;
+  if (float* alias = pinned_alias(out_sdf)) {     // pinned caller buffer: the kernel writes the host grid directly
+    job.out_pred = alias;
+    if (run_job(c, job)) return -1;
+    DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return check_status(c);
+  }
+  if (ensure_scratch(c, (int64_t)B * N)) return -1;
   job.out_pred = c->d_out;
   if (run_job(c, job)) return -1;
   DISN_CUDA_OK(cudaMemcpyAsync(out_sdf, c->d_out, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_status(c);
 }
 
 int disn_write_dist(const char* path, int32_t res, const double* bbox, const float* values) {

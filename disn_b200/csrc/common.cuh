@@ -70,7 +70,7 @@ struct PointJob {
   const float* pmap;      // [B,img_h,img_w,512]
   int32_t img_h, img_w;
   float clamp_max;
-  float out_scale;        // 1 (eval_points) or 1/sdf_weight (eval_grid)
+  float out_div;          // result divisor: 1 (eval_points) or sdf_weight (eval_grid)
   int32_t tanh_out;
   StreamWeights g, l;
   // DISN_PREC_F16F8: power-of-two multipliers of the e5m2 correction operands, [stream][layer]{(a-h(a)) scale, a scale}
@@ -78,7 +78,10 @@ struct PointJob {
   // outputs
   float* out_pred;        // [B,N]
   float* out_uv;          // [B,N,2] or nullptr
+  int* status;            // device word the kernels OR failure bits into (DISN_STATUS_*), or nullptr
 };
+
+constexpr int DISN_STATUS_FP16_OVERFLOW = 1;   // DISN_PREC_F16F8: an activation exceeded fp16's range
 
 }  // namespace disn
 
@@ -89,6 +92,8 @@ struct disn_ctx {
   std::map<std::string, disn::DevTensor> weights;
   bool weights_dirty = true;
   int64_t launches = 0;
+  int num_sms = 148;            // cudaDevAttrMultiProcessorCount of cfg.device, read once in disn_create
+  bool attr_conv_tc = false, attr_point_fp32 = false, attr_point_tc[4] = {false, false, false, false};   // cudaFuncSetAttribute done on this device
 
   // encoder state
   int32_t enc_B = 0;
@@ -106,10 +111,15 @@ struct disn_ctx {
   float* emb = nullptr;         // [B,num_classes]
   float* gbias = nullptr;       // [B,512]
   float* pmap = nullptr;        // [B,img_h,img_w,512]
+  cudaGraphExec_t enc_graph_exec = nullptr;   // captured encoder launch sequence (encoder_run)
+  std::vector<int64_t> enc_graph_key, enc_warm_key;
+  int64_t enc_graph_launches = 0;
   // scratch for host-pointer calls
   float* d_pts = nullptr; float* d_pts_rot = nullptr; float* d_out = nullptr; float* d_uv = nullptr;
   int64_t scratch_pts = 0;
   float* d_tm = nullptr;        // [max_batch,4,3]
+  int* d_status = nullptr;      // device status word (PointJob::status)
+  int* h_status = nullptr;      // pinned host mirror, copied behind every point-kernel launch
   float* d_axes = nullptr;      // [max_batch,3,R]
   int32_t axes_R = 0;
   std::vector<double> axes_key; // (sdf_params, R) the tables in d_axes were built from
@@ -119,7 +129,7 @@ struct disn_ctx {
   void* tc_weights_f8 = nullptr;       // fp16 + e5m2 stage images (DISN_PREC_F16F8)
   float tc_act_scale[2][4][2] = {};
   bool tc_small_ok = false;
-  float tc_small[2][2048] = {};         // host copy of the per-stream small parameters (experimental v2 kernel's parameter table)
+  float tc_small[2][2048] = {};         // host copy of the per-stream small parameters (the point kernel's __grid_constant__ table)
   std::map<std::string, uint8_t*> enc_tc_weights;   // packed bf16 hi/lo stage images of the encoder GEMMs
 };
 
@@ -129,12 +139,12 @@ int encoder_alloc(disn_ctx* c, int B);
 int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool device_ptr,
                 bool embedding_only = false);
 void encoder_free(disn_ctx* c);
+void encoder_graph_reset(disn_ctx* c);
 // point_fp32.cu
 int launch_point_fp32(disn_ctx* c, const PointJob& job);
 // point_tc.cu
 int tc_pack_weights(disn_ctx* c);
 int launch_point_tc(disn_ctx* c, const PointJob& job);
-int launch_point_tc_v2(disn_ctx* c, const PointJob& job);   // experimental (DISN_TC_V2=1), point_tc_v2.cu
 // conv_tc.cu
 int conv_tc_pack(disn_ctx* c, const float* d_w, int K, int N, uint8_t** out_dev);
 int launch_conv_tc(disn_ctx* c, const float* A, const uint8_t* wpk, const float* bias, float* C, float* ws,

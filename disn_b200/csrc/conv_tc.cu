@@ -277,14 +277,12 @@ int conv_tc_pack(disn_ctx* c, const float* d_w, int K, int N, uint8_t** out_dev)
 int launch_conv_tc(disn_ctx* c, const float* A, const uint8_t* wpk, const float* bias, float* C, float* ws,
                    int64_t ws_elems, int M, int N, int K, int H, int W, int Cin, int relu, int* splits_out) {
   DISN_REQUIRE(K % 64 == 0 && N % 32 == 0 && (H == 0 || Cin % 64 == 0), "conv_tc: K%64, N%32, Cin%64");
-  static bool attr_set = false;
   const int smem = (int)sizeof(ConvTcSmem) + 1024;
-  if (!attr_set) {
+  if (!c->attr_conv_tc) {    // per context (= per device): the attribute is a property of the function ON a device
     DISN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    c->attr_conv_tc = true;
   }
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
+  const int sms = c->num_sms;
   ConvTcJob job{};
   job.A = A; job.wpk = wpk; job.bias = bias; job.C = C; job.M = M; job.N = N; job.K = K;
   job.H = H; job.W = W; job.Cin = Cin; job.relu = relu;

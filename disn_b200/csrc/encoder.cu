@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace disn {
@@ -411,7 +413,10 @@ static const char* kConvName[kNumConv] = {
     "vgg_16/conv5/conv5_3"};
 static const int kTapHW[5] = {224, 112, 56, 28, 14};
 
+void encoder_graph_reset(disn_ctx* c);
+
 void encoder_free(disn_ctx* c) {
+  encoder_graph_reset(c);      // the captured graph holds these buffers' addresses
   auto fr = [](float*& p) { if (p) cudaFree(p); p = nullptr; };
   fr(c->img_in); fr(c->img_rs); fr(c->act[0]); fr(c->act[1]);
   for (int i = 0; i < 5; ++i) { fr(c->taps[i]); fr(c->proj[i]); }
@@ -490,12 +495,66 @@ static const float* wptr(disn_ctx* c, const std::string& name) {
   return it == c->weights.end() ? nullptr : it->second.ptr;
 }
 
+static int encoder_body(disn_ctx* c, int B, int H, int W, int C, bool embedding_only);
+
+// The encoder is ~50 small launches (13 convs with split-K reduces, pools, GEMVs, 5 projections, the map fold): at B = 1
+// their GPU time is ~0.5 ms but the launch gaps made it ~3 ms per step.  After one eager run per shape (which also packs
+// the tcgen05 weight images), the launch sequence is captured into a CUDA graph and replayed with one cudaGraphLaunch.
+void encoder_graph_reset(disn_ctx* c) {
+  if (c->enc_graph_exec) cudaGraphExecDestroy(c->enc_graph_exec);
+  c->enc_graph_exec = nullptr;
+  c->enc_graph_key.clear();
+  c->enc_warm_key.clear();
+}
+
 int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool device_ptr, bool embedding_only) {
   DISN_REQUIRE(C == 3, "imgs must have 3 channels (FLAGS.alpha is not on the hot path)");
   DISN_REQUIRE(B >= 1 && B <= GEMV_MAXB, "batch must be in [1,8]");
-  const int V = c->cfg.vgg_in;
-  DISN_REQUIRE((int64_t)H * W <= (int64_t)V * V * 4 / 3, "input image too large");
+  DISN_REQUIRE((int64_t)H * W <= (int64_t)c->cfg.vgg_in * c->cfg.vgg_in * 4 / 3, "input image too large");
   if (encoder_alloc(c, B)) return -1;
+  DISN_CUDA_OK(cudaMemcpyAsync(c->img_in, imgs, (size_t)B * H * W * C * sizeof(float),
+                               device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  const std::vector<int64_t> key = {B, H, W, C, (int64_t)embedding_only, (int64_t)c->cfg.precision};
+  static const bool no_graph = getenv("DISN_NO_GRAPH") != nullptr;
+  if (!no_graph && c->enc_graph_exec && key == c->enc_graph_key) {
+    DISN_CUDA_OK(cudaGraphLaunch(c->enc_graph_exec, c->stream));
+    c->launches += c->enc_graph_launches;
+    c->enc_B = embedding_only ? 0 : B;
+    return 0;
+  }
+  if (no_graph || key != c->enc_warm_key) {      // first time with this shape: eager (packs weights, sets attributes)
+    const int rc = encoder_body(c, B, H, W, C, embedding_only);
+    if (rc == 0) c->enc_warm_key = key;
+    return rc;
+  }
+  // second time: capture, instantiate, replay
+  if (c->enc_graph_exec) { cudaGraphExecDestroy(c->enc_graph_exec); c->enc_graph_exec = nullptr; c->enc_graph_key.clear(); }
+  const int64_t l0 = c->launches;
+  DISN_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = encoder_body(c, B, H, W, C, embedding_only);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+  c->enc_graph_launches = c->launches - l0;
+  c->launches = l0;
+  if (rc != 0 || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    c->enc_B = 0;
+    if (rc == 0) set_error(std::string("encoder graph capture failed: ") + cudaGetErrorString(ce));
+    return -1;
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&c->enc_graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { c->enc_graph_exec = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return -1; }
+  c->enc_graph_key = key;
+  DISN_CUDA_OK(cudaGraphLaunch(c->enc_graph_exec, c->stream));
+  c->launches += c->enc_graph_launches;
+  c->enc_B = embedding_only ? 0 : B;
+  return 0;
+}
+
+static int encoder_body(disn_ctx* c, int B, int H, int W, int C, bool embedding_only) {
+  const int V = c->cfg.vgg_in;
   for (int i = 0; i < kNumConv; ++i) {
     DISN_REQUIRE(wptr(c, std::string(kConvName[i]) + "/weights") && wptr(c, std::string(kConvName[i]) + "/biases"),
                  std::string("missing weights for ") + kConvName[i]);
@@ -507,8 +566,6 @@ int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool
                  std::string("missing weights for ") + nm);
   }
 
-  DISN_CUDA_OK(cudaMemcpyAsync(c->img_in, imgs, (size_t)B * H * W * C * sizeof(float),
-                               device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   const float* x = c->img_in;
   if (H != V || W != V) {  // model_normalization.py:65-72
     resize_bilinear_tf_kernel<<<592, 256, 0, c->stream>>>(c->img_in, c->img_rs, B, H, W, C, V, V);

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_fp32_kernel(PointJob job, i
           if (n < job.N) {
             float r = s.pred[p] + (sum + job.l.b6[0]);     // pred_sdf = global + local (:204)
             if (job.tanh_out) r = tanhf(r);
-            job.out_pred[(int64_t)b * job.N + n] = r * job.out_scale;
+            job.out_pred[(int64_t)b * job.N + n] = __fdiv_rn(r, job.out_div);
           }
         }
       }
@@ -280,18 +280,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_fp32_kernel(PointJob job, i
 }  // namespace
 
 int launch_point_fp32(disn_ctx* c, const PointJob& job) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!c->attr_point_fp32) {   // per context (= per device)
     DISN_CUDA_OK(cudaFuncSetAttribute(point_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(Smem)));
-    attr_set = true;
+    c->attr_point_fp32 = true;
   }
   int64_t tiles_per_img = (job.N + TP - 1) / TP;
   int64_t total = tiles_per_img * job.B;
   if (total == 0) return 0;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
-  int grid = (int)std::min<int64_t>(total, sms);
+  int grid = (int)std::min<int64_t>(total, c->num_sms);
   point_fp32_kernel<<<grid, NTHREADS, sizeof(Smem), c->stream>>>(job, tiles_per_img);
   c->launches++;
   DISN_CUDA_OK(cudaGetLastError());

@@ -15,23 +15,27 @@
 //     epilogue warps (bias / folded image features, ReLU, operand split) into a 3-slot ring of
 //     K-major swizzled A tiles that layer l+1's MMAs consume (K-outer), so MMA and epilogue pipeline; for the 512-wide
 //     layers each N-block has its own "accumulator complete" barrier, so draining starts while the other block runs;
-//   * the two streams are skewed by one layer: the MMA warp issues L0 of stream n+1 (one stage) before L3 of stream n,
+//     fold1/conv1 (3 -> 64, fp32 FMA) is staged into the same ring by epilogue group 0 from the points the front end
+//     publishes, in the ring position the issue order needs (... X4_n, X2_{n+1}, X5_n, X3_{n+1} ...);
+//   * the two streams are skewed by one layer: L0 of stream n+1 (one stage) is issued before L3 of stream n,
 //     into the 128 TMEM columns that are free then (even/odd streams use mirrored column maps, acc_col()), so the next
-//     stream's first drain overlaps this stream's last layer; the front end stages fold1/conv1 one stream ahead;
+//     stream's first drain overlaps this stream's last layer;
 //   * weights are pre-split, pre-permuted and pre-swizzled on the host into the exact shared-memory images the
-//     B operand needs (32 KB per (K-slice, N-block) and CTA), packed in the MMA warp's consumption order, and streamed
-//     by the bulk-copy engine (cp.async.bulk) through a 3-slot mbarrier ring; each CTA loads only its half of every
-//     B tile, the peer relays its arrival to the leader.  On a busy SM an mbarrier operation costs the issuing thread
-//     100-250 cycles, so each ring slot has its own producer warp and the stage is as large as shared memory allows;
-//   * warp roles: 0,2,3 weight producers (2 also allocates TMEM), 1 MMA issuer (leader CTA; warp-uniform loop,
-//     one elected lane issues), 4-11 epilogue in two groups taking alternate slices (one warp per TMEM lane quarter
-//     in each group), 12-15 front end (points, projection, layer 1, bilinear gather of the projected feature map into
-//     a shared-memory ring);
-//   * every mbarrier is waited on, phase after phase, by the same agent(s): a parity wait is only meaningful for a
-//     waiter that has observed every earlier phase of that barrier (tools/tc_protocol_sim.py models the protocol);
-//   * DISN_TC_TRACE=1 runs an instrumented instantiation that accounts the cycles every role spends blocked
-//     on each barrier class (profiles/*_tc_wait_trace.txt); DISN_TC_TIMELINE=<file> adds a one-tile event timeline
-//     (tools/tc_timeline.py), DISN_TC_EXPT=<mask> skips MMA groups in the instrumented build.
+//     B operand needs (32 KB per (K-slice, N-block) and CTA), packed in consumption order, and streamed
+//     by the bulk-copy engine (cp.async.bulk) through a 4-slot mbarrier ring; each CTA loads only its half of every
+//     B tile; producers (warps 0 and 2) own fixed slots, never wait for the data and post the byte count after issuing
+//     the copies; on the peer CTA warp 1 forwards "my half landed" to the leader;
+//   * two MMA issuer warps on the leader CTA (warp 1: N-block 0 and all single-block layers, warp 3: N-block 1;
+//     warp-uniform loops, one elected lane issues).  Their accumulators are disjoint, so the summation order and the
+//     results stay bitwise deterministic.  One "stage landed" barrier per (issuer, slot): a stage's copies signal the
+//     barrier of the issuer that will consume it (static stage -> issuer map), so every barrier is waited on, phase
+//     after phase, by one agent only (a parity wait is meaningless for a waiter that skipped a phase; the protocol is
+//     modelled in tools/tc_protocol_sim.py: x2_in_ring=1, NW=4, issuers=2, split_wfull=1);
+//   * warps 4-11 epilogue in two groups taking alternate slices (one warp per TMEM lane quarter in each group),
+//     warps 12-15 front end (points, projection, bilinear gather of the projected feature map into a shared-memory ring);
+//   * the small per-stream parameters (biases, fold1/conv1, fold2/conv5) are a __grid_constant__ kernel parameter
+//     (constant bank, warp-uniform indexed loads).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -47,65 +51,89 @@
 namespace disn {
 namespace {
 
-constexpr int NW = 3;                 // weight ring stages == weight producer warps (each owns one slot)
+constexpr int NW = 4;                 // weight ring stages
 #include "point_tc_shared.cuh"
+
+constexpr int RING_PER_STREAM = 21;   // X3 (4) + X4 (8) + next stream's X2 (1) + X5 (8)
+
+struct SmallParams { float v[2][SB_STRIDE]; };   // per stream: b2 b3 b4 b5 w6 w1 b1 at the SB_* offsets
+
 struct TcSmem {
   alignas(1024) uint8_t w[NW][W_STAGE];
-  alignas(1024) uint8_t x[NX][2][X_HALF];      // [slot][hi|lo]  ring written by the epilogue warps
-  alignas(1024) uint8_t x2[2][X_HALF];         // fold1/conv1 output (layer-2 A operand) written by the front end
+  alignas(1024) uint8_t x[NX][2][X_HALF];      // activation ring (all four tensor-core layers' A operands)
   float g[NG][64 * G_LD];                      // gathered image features [h*32+j][point]
-  float sb[2][SB_STRIDE];                      // per-stream small parameters (biases, fold2/conv5, fold1/conv1)
-  float px[2][PTS], py[2][PTS], pz[2][PTS];    // by tile parity (the front end runs one tile ahead for fold1/conv1)
+  float px[2][PTS], py[2][PTS], pz[2][PTS];    // query points by tile parity
   int tap_off[2][PTS][4];
   float tap_w[2][PTS][4];
   float part[2][2][2][2][PTS];                 // [tile parity][stream][half][epilogue group][point]
-  alignas(8) uint64_t wfull[NW];
+  alignas(8) uint64_t wfull[2][NW];           // [consuming issuer][slot]   (peer CTA: only [0][slot], for the relay)
   uint64_t wempty[NW];
   uint64_t xfull[NX];
   uint64_t xempty[NX];
-  uint64_t x2full;
-  uint64_t x2empty;
+  uint64_t pfull[2];                           // points of tile parity published by the front end
   uint64_t gfull[NG];
   uint64_t gempty[NG];
-  uint64_t acc_full[4][2];                     // [layer][N-block]: committed right after the block's last MMAs
+  uint64_t acc_full[4][2];
   uint64_t acc5_free;
   uint32_t tmem_base;
 };
 
-template <bool kTrace, int kMode>
+// issuer (0/1) that consumes weight stage `g` of the consumption sequence (g = 0: first stream's L0; then the per-tile cycle
+// G.L1(8) G.L2(16) L.L0(1) G.L3(8) L.L1(8) L.L2(16) G.L0(1) L.L3(8); the last tile has no G.L0 entry)
+__device__ __forceinline__ void stage_info(uint32_t g, int my_tiles, uint32_t& img_stage, int& issuer) {
+  img_stage = FIRST_L0_POS;
+  issuer = 0;
+  if (g == 0) return;
+  const uint32_t cidx = g - 1, last0 = (uint32_t)(my_tiles - 1) * (2 * STAGES_PER_STREAM);
+  uint32_t r = cidx % (2 * STAGES_PER_STREAM);
+  if (cidx >= last0 && cidx - last0 >= (uint32_t)FIRST_L0_POS) r = cidx - last0 + 1;
+  img_stage = r;
+  if (r < 24) issuer = (int)(r & 1u);                    // G.L1, G.L2: N-blocks alternate
+  else if (r >= 33 && r < 57) issuer = (int)((r - 33) & 1u);   // L.L1, L.L2
+}
+
+// position of an activation slice in the ring: kind 2 = fold1/conv1 output of stream sn, 3/4/5 = outputs of tensor-core
+// layers 0/1/2 of stream sn (tools/tc_protocol_sim.py: seq_of)
+__device__ __forceinline__ uint32_t ring_seq(int sn, int kind, int t, int nstreams) {
+  if (kind == 2) return sn == 0 ? 0u : (uint32_t)(1 + RING_PER_STREAM * (sn - 1) + 12);
+  const uint32_t base = 1u + (uint32_t)RING_PER_STREAM * (uint32_t)sn;
+  if (kind == 5) return base + 12u + (sn + 1 < nstreams ? 1u : 0u) + (uint32_t)t;
+  return base + (kind == 3 ? 0u : 4u) + (uint32_t)t;
+}
+
+// kVar bit 0: measurement build -- `expt` masks MMA groups (1 main product, 2 first correction, 4 second correction) and
+//             every CTA reports its cycle count (DISN_TC_MEASURE=1 [DISN_TC_EXPT=<mask>]; masked results are wrong by
+//             construction).  The product build (kVar = 0) carries none of it.
+#define WAIT(bar, par) tc::mbar_wait(bar, par)
+template <int kMode, int kVar>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per_img,
-                unsigned long long* __restrict__ dbg, int expt) {
+point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint8_t* __restrict__ wpk,
+                 int64_t tiles_per_img, unsigned long long* __restrict__ dbg, int expt) {
   extern __shared__ uint8_t smem_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const uint32_t cta = tc::cluster_ctarank();
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
   const int num_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int64_t total_tiles = tiles_per_img * job.B;
   const int my_tiles = (pair < total_tiles) ? (int)((total_tiles - pair + num_pairs - 1) / num_pairs) : 0;
+  const int nstreams = 2 * my_tiles;
+  const uint32_t total_stages = (uint32_t)my_tiles * (2 * STAGES_PER_STREAM);
 
   if (tid == 0) {
-    for (int i = 0; i < NW; ++i) { tc::mbar_init(&s.wfull[i], cta == 0 ? 2 : 1); tc::mbar_init(&s.wempty[i], 1); }
-    for (int i = 0; i < NX; ++i) { tc::mbar_init(&s.xfull[i], 8); tc::mbar_init(&s.xempty[i], 1); }
-    tc::mbar_init(&s.x2full, 8);
-    tc::mbar_init(&s.x2empty, 1);
+    for (int i = 0; i < NW; ++i) {
+      // leader: {its producer's expect_tx arrival, the peer relay's arrival}; peer: {its producer's expect_tx arrival}
+      tc::mbar_init(&s.wfull[0][i], cta == 0 ? 2 : 1);
+      tc::mbar_init(&s.wfull[1][i], cta == 0 ? 2 : 1);
+      tc::mbar_init(&s.wempty[i], 1);
+    }
+    for (int i = 0; i < NX; ++i) { tc::mbar_init(&s.xfull[i], 8); tc::mbar_init(&s.xempty[i], 2); }
+    tc::mbar_init(&s.pfull[0], 1);
+    tc::mbar_init(&s.pfull[1], 1);
     for (int i = 0; i < NG; ++i) { tc::mbar_init(&s.gfull[i], 4); tc::mbar_init(&s.gempty[i], 4); }
     for (int i = 0; i < 4; ++i) { tc::mbar_init(&s.acc_full[i][0], 1); tc::mbar_init(&s.acc_full[i][1], 1); }
     tc::mbar_init(&s.acc5_free, 16);
     tc::fence_barrier_init();
-  }
-  for (int i = tid; i < 2 * SB_STRIDE; i += NTHREADS) {   // small parameters -> shared memory, once
-    const StreamWeights& w = (i >= SB_STRIDE) ? job.l : job.g;
-    const int o = i % SB_STRIDE;
-    float v;
-    if (o < SB_B3) v = w.b2[o - SB_B2];
-    else if (o < SB_B4) v = w.b3[o - SB_B3];
-    else if (o < SB_B5) v = w.b4[o - SB_B4];
-    else if (o < SB_W6) v = w.b5[o - SB_B5];
-    else if (o < SB_W1) v = w.w6[o - SB_W6];
-    else if (o < SB_B1) v = w.w1[o - SB_W1];
-    else v = w.b1[o - SB_B1];
-    s.sb[i / SB_STRIDE][o] = v;
   }
   __syncthreads();
   if (warp == 2) {
@@ -116,180 +144,129 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
   tc::cluster_sync();
   tc::tc_fence_after_sync();
   const uint32_t tmem = s.tmem_base;
-  // optional wait-time accounting (DISN_TC_TRACE=1): cycles each role spends blocked on each barrier class
-  unsigned long long wt[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [6 + sidx*4 + layer]: MMA warp's activation waits
-  const long long t_role0 = kTrace ? clock64() : 0;
-#define TIMED_WAIT(slot, call)                          \
-  do {                                                  \
-    if constexpr (kTrace) {                             \
-      const long long _t = clock64();                   \
-      call;                                             \
-      wt[slot] += (unsigned long long)(clock64() - _t); \
-    } else {                                            \
-      call;                                             \
-    }                                                   \
-  } while (0)
+  const long long t_start = (kVar & 1) ? clock64() : 0;
 
-  // timeline of one tile of CTA 0 (trace build): raw clock64 stamps, decoded by tools/tc_timeline.py
-  unsigned long long* tl = dbg ? dbg + (size_t)gridDim.x * 24 : nullptr;
-#define TL(it_, idx)                                                                         \
-  do {                                                                                       \
-    if constexpr (kTrace) {                                                                  \
-      if (blockIdx.x == 0 && (it_) == 4 && lane == 0) tl[idx] = (unsigned long long)clock64(); \
-    }                                                                                        \
-  } while (0)
-
-  if (warp == 0 || warp == 2 || warp == 3) {
-    // ===================== weight producers (bulk-copy engine): three warps, one ring slot each =============
-    // An mbarrier op costs the issuing thread ~200 cycles, so one producer thread cannot feed the MMAs;
-    // slot pw is filled, (in the peer CTA) relayed to the leader, and refilled by the same warp.
-    static_assert(NW == 3, "one producer warp per ring slot");
-    const int pw = (warp == 0) ? 0 : warp - 1;
-    if (lane < 2) {          // two lanes issue one 16 KB tile each (hi / lo) so the copies overlap
-      const uint32_t total_stages = (uint32_t)my_tiles * (2 * STAGES_PER_STREAM);
-      if (lane == 0 && (uint32_t)pw < total_stages) tc::mbar_arrive_expect_tx(&s.wfull[pw], W_STAGE);
-      __syncwarp(0x3);
-      for (uint32_t g = pw; g < total_stages; g += NW) {
-        const uint32_t use = g / NW;
-        tc::mbar_wait(&s.wempty[pw], (use & 1) ^ 1);
-        // consumption order -> position in the packed per-tile cycle; the last tile has no "next stream" L0 stage
-        uint32_t img_stage = FIRST_L0_POS;
-        if (g > 0) {
-          const uint32_t cidx = g - 1, last0 = (uint32_t)(my_tiles - 1) * (2 * STAGES_PER_STREAM);
-          img_stage = cidx % (2 * STAGES_PER_STREAM);
-          if (cidx >= last0 && cidx - last0 >= (uint32_t)FIRST_L0_POS) img_stage = cidx - last0 + 1;
-        }
-        const uint8_t* src = wpk + (size_t)img_stage * (2 * W_STAGE) + (size_t)cta * W_STAGE +
-                             (size_t)lane * W_TILE;
-        tc::bulk_g2s(s.w[pw] + lane * W_TILE, src, W_TILE, &s.wfull[pw]);
-        tc::mbar_wait(&s.wfull[pw], use & 1);     // leader: own bytes + peer relay; peer: own bytes
-        if (lane == 0) {
-          if (cta == 1) tc::mbar_arrive_cluster(&s.wfull[pw], 0);   // leader's wfull counts {own expect_tx, this arrive}
-          // pre-post the next use's transaction count so that only the copy issue follows the slot release
-          if (g + NW < total_stages) tc::mbar_arrive_expect_tx(&s.wfull[pw], W_STAGE);
-        }
+  if (warp == 0 || warp == 2) {
+    // ===================== weight producers: warp 0 = even stages (slots 0, 2), warp 2 = odd stages (slots 1, 3) ==========
+    const uint32_t pw = (warp == 0) ? 0u : 1u;
+    if (lane < 2) {          // two lanes issue one 16 KB tile each so the copies overlap
+      for (uint32_t g = pw; g < total_stages; g += 2) {
+        const uint32_t slot = g % NW, use = g / NW;
+        WAIT(&s.wempty[slot], (use & 1) ^ 1);
+        uint32_t img_stage;
+        int issuer;
+        stage_info(g, my_tiles, img_stage, issuer);
+        uint64_t* bar = &s.wfull[cta == 0 ? issuer : 0][slot];
+        const uint8_t* src = wpk + (size_t)img_stage * (2 * W_STAGE) + (size_t)cta * W_STAGE + (size_t)lane * W_TILE;
+        tc::bulk_g2s(s.w[slot] + lane * W_TILE, src, W_TILE, bar);
+        // the byte count may be posted after the copies: the phase cannot complete before this arrival
+        if (lane == 0) tc::mbar_arrive_expect_tx(bar, W_STAGE);
         __syncwarp(0x3);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && cta == 1) {
+    // ===================== peer CTA: forward "my half of the stage has landed" to the consuming issuer's barrier ==========
+    if (lane == 0) {
+      for (uint32_t g = 0; g < total_stages; ++g) {
+        const uint32_t slot = g % NW;
+        uint32_t img_stage;
+        int issuer;
+        stage_info(g, my_tiles, img_stage, issuer);
+        WAIT(&s.wfull[0][slot], (g / NW) & 1);
+        tc::mbar_arrive_cluster(&s.wfull[issuer][slot], 0);
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
     if (cta == 0) {
-      // ===================== MMA issuer (leader CTA) =====================
-      // The whole warp runs the loop so every address/descriptor is warp-uniform (uniform registers);
-      // a single elected lane issues the tcgen05 instructions.
+      // ===================== MMA issuers (leader CTA): warp 1 = N-block 0 + single-block layers, warp 3 = N-block 1 =========
+      // Warp-uniform loop, one elected lane issues.  Both issuers wait for every activation slice (that keeps them within
+      // one ring of each other and orders their TMEM writes after the epilogue's reads) and both release it (xempty = 2).
+      const int which = (warp == 3) ? 1 : 0;
       const uint32_t idesc = (kMode == MODE_BF16X3) ? tc::make_idesc_bf16(128, 256) : tc::make_idesc_f16(128, 256);
       const uint32_t idesc8 = tc::make_idesc_e5m2(128, 256);
-      const uint32_t w_lo0 = tc::desc_lo(tc::smem_u32(s.w[0]));          // + st * (W_STAGE >> 4)
-      const uint32_t x_lo0 = tc::desc_lo(tc::smem_u32(s.x[0][0]));       // + slot * (2*X_HALF >> 4), lo = + X_HALF >> 4
-      const uint32_t x2_lo0 = tc::desc_lo(tc::smem_u32(s.x2[0]));
-      uint32_t xseq = 0, nstream = 0;
-      uint32_t wst = 0, wph = 0;      // weight ring slot / phase parity
-      uint32_t xsl = 0, xph = 0;      // activation ring slot / phase parity
-      // Issue order (streams skewed by one layer): L0(0); then per stream n: L1(n) L2(n) L0(n+1) L3(n).  The next stream's
-      // first layer is tiny (one stage); hoisting it lets its drain overlap L3(n)'s MMAs, so L1(n+1) follows L3(n)
-      // without the accumulator round trip.
-      const int nstreams = 2 * my_tiles;
+      const uint32_t w_lo0 = tc::desc_lo(tc::smem_u32(s.w[0]));
+      const uint32_t x_lo0 = tc::desc_lo(tc::smem_u32(s.x[0][0]));
+      uint32_t g = 0;                       // weight stage counter (consumption order, all stages of both issuers)
+      uint32_t wuse[NW] = {0, 0, 0, 0};    // this issuer's uses of each slot so far (phase of its own barrier)
+      uint32_t xsl = 0, xph = 0;            // activation ring slot / phase parity
       for (int grp = -1; grp < nstreams; ++grp) {
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           const int layer = (q == 0) ? 1 : (q == 1 ? 2 : (q == 2 ? 0 : 3));
           const int sn = (q == 2) ? grp + 1 : grp;
           if (sn < 0 || sn >= nstreams) continue;
-          nstream = (uint32_t)sn;
-          const int sidx = sn & 1, it = sn >> 1;
-          {
-            const int nsl = (layer == 0) ? 1 : (layer == 1 ? 4 : 8);
-            const int nnb = (layer == 1 || layer == 2) ? 2 : 1;
-            const uint32_t colbase = acc_col(layer, sidx);
-            if (layer == 2 && nstream > 0) {   // acc4 overwrites the columns the previous stream's acc5 used
-              TIMED_WAIT(2, tc::mbar_wait(&s.acc5_free, (nstream - 1) & 1));
-              tc::tc_fence_after_sync();
-            }
+          const int sidx = sn & 1;
+          const int nsl = (layer == 0) ? 1 : (layer == 1 ? 4 : 8);
+          const int nnb = (layer == 1 || layer == 2) ? 2 : 1;
+          const uint32_t colbase = acc_col(layer, sidx);
+          if (layer == 2 && sn > 0) {        // acc4 overwrites the columns the previous stream's acc5 used
+            WAIT(&s.acc5_free, (uint32_t)(sn - 1) & 1);
+            tc::tc_fence_after_sync();
+          }
 #pragma unroll 1
-            for (int t = 0; t < nsl; ++t) {
-              const uint32_t slot = xsl;
-              uint32_t a_hi;
-              if (layer == 0) {      // A operand = layer-1 output staged by the front end
-                TIMED_WAIT(6 + sidx * 4 + layer, tc::mbar_wait(&s.x2full, nstream & 1));
-                a_hi = x2_lo0;
-              } else {
-                TIMED_WAIT(6 + sidx * 4 + layer, tc::mbar_wait(&s.xfull[slot], xph));
-                a_hi = x_lo0 + (uint32_t)slot * ((2 * X_HALF) >> 4);
-              }
-              const uint32_t a_lo = a_hi + (X_HALF >> 4);
+          for (int t = 0; t < nsl; ++t) {
+            const uint32_t slot = xsl;
+            WAIT(&s.xfull[slot], xph);
+            tc::tc_fence_after_sync();
+            const uint32_t a_hi = x_lo0 + slot * ((2 * X_HALF) >> 4);
+            const uint32_t a_lo = a_hi + (X_HALF >> 4);
+            const int nb = (nnb == 2) ? which : 0;
+            const bool mine = (nnb == 2) || which == 0;
+            if (mine) {
+              const uint32_t st = (g + (uint32_t)nb) % NW;
+              WAIT(&s.wfull[which][st], wuse[st] & 1);
+              ++wuse[st];
               tc::tc_fence_after_sync();
-              const int sl = sidx * 21 + (layer == 0 ? 0 : layer == 1 ? 1 + t : layer == 2 ? 5 + t : 13 + t);
-              TL(it, 0 + sl);                 // A slice acquired
-#pragma unroll 1
-              for (int nb = 0; nb < nnb; ++nb) {
-                const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
-                const uint32_t st = wst;
-                TIMED_WAIT(0, tc::mbar_wait(&s.wfull[st], wph));
-                tc::tc_fence_after_sync();
-                const uint32_t b_hi = w_lo0 + (uint32_t)st * (W_STAGE >> 4);
-                const uint32_t b_lo = b_hi + (W_TILE >> 4);
-                const long long ti = kTrace ? clock64() : 0;
-                if (tc::elect_one()) {
-                  if constexpr (kMode == MODE_BF16X3) {
+              const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
+              const uint32_t b_hi = w_lo0 + st * (W_STAGE >> 4);
+              const uint32_t b_lo = b_hi + (W_TILE >> 4);
+              if (tc::elect_one()) {
+                if constexpr (kMode == MODE_BF16X3) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_lo + 2u * k, b_hi + 2u * k, idesc, 1u);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
+                } else {
+                  const bool x0 = !(kVar & 1) || !(expt & 1), x1 = !(kVar & 1) || !(expt & 2), x2 = !(kVar & 1) || !(expt & 4);
+                  if (x0) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_lo + 2u * k, b_hi + 2u * k, idesc, 1u);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
-                  } else {
-                    // a_hi = fp16 A tile, a_lo = e5m2 residual tile (+X8_TILE: e5m2 copy of a); b_hi = fp16 W tile,
-                    // b_lo = e5m2 copy of w (+W8_TILE: e5m2 residual of w)
-                    const bool x0 = !kTrace || !(expt & 1), x1 = !kTrace || !(expt & 2), x2 = !kTrace || !(expt & 4);
-                    if (x0) {
-#pragma unroll
-                      for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
-                    }
-                    if (x1) {
-#pragma unroll
-                      for (int k = 0; k < 2; ++k) tc::mma_cg2_f8_lo(d, a_lo + 2u * k, b_lo + 2u * k, idesc8, 1u);
-                    }
-                    if (x2) {
-#pragma unroll
-                      for (int k = 0; k < 2; ++k)
-                        tc::mma_cg2_f8_lo(d, a_lo + (X8_TILE >> 4) + 2u * k, b_lo + (W8_TILE >> 4) + 2u * k, idesc8, 1u);
-                    }
                   }
-                  tc::commit_cg2(&s.wempty[st], 0b11);
-                  // the block's accumulator is final after its last K slice: let the epilogue start on it while the
-                  // other N-block's MMAs still run
-                  if (t == nsl - 1) tc::commit_cg2(&s.acc_full[layer][nb], 0b11);
-                  if (nb == nnb - 1) {               // the slice's A tile is free once all of its MMAs retire
-                    if (layer == 0) tc::commit_cg2(&s.x2empty, 0b11);
-                    else tc::commit_cg2(&s.xempty[slot], 0b11);
+                  if (x1) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) tc::mma_cg2_f8_lo(d, a_lo + 2u * k, b_lo + 2u * k, idesc8, 1u);
+                  }
+                  if (x2) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                      tc::mma_cg2_f8_lo(d, a_lo + (X8_TILE >> 4) + 2u * k, b_lo + (W8_TILE >> 4) + 2u * k, idesc8, 1u);
                   }
                 }
-                if constexpr (kTrace) wt[1] += (unsigned long long)(clock64() - ti);
-                if (++wst == NW) { wst = 0; wph ^= 1u; }
+                tc::commit_cg2(&s.wempty[st], 0b11);
+                if (t == nsl - 1) tc::commit_cg2(&s.acc_full[layer][nb], 0b11);
+                tc::commit_cg2(&s.xempty[slot], 0b11);     // second arrival comes from the other issuer
               }
-              TL(it, 64 + sl);                // slice issued + released
-              if (layer != 0) { ++xseq; if (++xsl == NX) { xsl = 0; xph ^= 1u; } }
+            } else {
+              // single-block layer, issuer 1: nothing to issue; its arrival only completes the slice's release count
+              if (tc::elect_one()) tc::commit_cg2(&s.xempty[slot], 0b11);
             }
-            TL(it, 128 + sidx * 4 + layer);   // layer committed
+            g += (uint32_t)nnb;
+            if (++xsl == NX) { xsl = 0; xph ^= 1u; }
           }
         }
       }
-      if (kTrace && lane == 0) {
-        unsigned long long* o = dbg + (size_t)blockIdx.x * 24;
-        o[0] = (unsigned long long)(clock64() - t_role0); o[1] = wt[0]; o[3] = wt[2];
-        unsigned long long act = 0;
-        for (int k = 0; k < 8; ++k) { o[8 + k] = wt[6 + k]; act += wt[6 + k]; }
-        o[2] = act; o[4] = wt[1]; o[16] = wt[3]; o[17] = wt[4];
-      }
     }
   } else if (warp >= 4 && warp < 12) {
-    // ===================== epilogue: TMEM -> bias/ReLU/split -> A-tile ring =====================
-    // two groups of four warps (one warp per TMEM lane quarter each); group eg drains the slices of its parity
+    // ===================== epilogue: TMEM -> bias/ReLU/split -> activation ring (two groups, alternate slices) ==========
     const int eg = (warp >= 8) ? 1 : 0;
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
     const int p = row & 63, h = row >> 6;
     const uint32_t tlane = tmem + ((uint32_t)(ew * 32) << 16);
     uint32_t gseq = 0;
+    __half2 amax = __float2half2_rn(0.f);   // running maximum of this thread's fp16 A-operand values (MODE_F16F8)
 
     auto arrive_xfull = [&](int slot) {
       tc::fence_proxy_async_smem();
@@ -299,104 +276,113 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         else tc::mbar_arrive_cluster(&s.xfull[slot], 0);
       }
     };
-    // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into activation slice `seq`
-    // (accbar != nullptr: first slice this group takes from that accumulator N-block)
-    auto drain = [&](uint32_t col0, int t, const float* bias, uint32_t seq, bool gather, float sc_lo, float sc_hi,
-                     uint64_t* accbar, uint32_t accpar) {
-      const int slot = seq % NX;
-      const int tli = 192 + (int)(seq % (2 * XSLOTS_PER_STREAM)) * 5, tit = (int)(seq / (2 * XSLOTS_PER_STREAM));
+    // fold1/conv1 (3 -> 64, fp32 FMA) of stream sn from the published points -> its ring slice (group 0 only)
+    auto stage_first = [&](int sn) {
+      const int tile = sn >> 1, sx = sn & 1;
+      const uint32_t seq = ring_seq(sn, 2, 0, nstreams);
+      const int slot = (int)(seq % NX);
+      WAIT(&s.pfull[tile & 1], (uint32_t)(tile >> 1) & 1);
+      const float x = s.px[tile & 1][p], y = s.py[tile & 1][p], z = s.pz[tile & 1][p];
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int f = h * 32 + j;
+        float a = sp.v[sx][SB_B1 + f];
+        a = fmaf(x, sp.v[sx][SB_W1 + f], a);
+        a = fmaf(y, sp.v[sx][SB_W1 + 64 + f], a);
+        a = fmaf(z, sp.v[sx][SB_W1 + 128 + f], a);
+        v[j] = fmaxf(a, 0.f);
+      }
+      WAIT(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
+      store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, job.act_scale[sx][0][0], job.act_scale[sx][0][1], amax);
+      arrive_xfull(slot);
+    };
+    // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into ring slice `seq`; the bias comes from the
+    // parameter table (sb_off, stream sx) or, for the global stream's fold2/conv1, from the per-image folded bias in HBM
+    auto drain = [&](uint32_t col0, int t, int sx, int sb_off, const float* gbias, uint32_t seq, bool gather, float sc_lo,
+                     float sc_hi, uint64_t* accbar, uint32_t accpar) {
+      const int slot = (int)(seq % NX);
       if (accbar) {
-        TIMED_WAIT(4, tc::mbar_wait(accbar, accpar));
+        WAIT(accbar, accpar);
         tc::tc_fence_after_sync();
       }
-      if (ew == 0) TL(tit, tli);
       uint32_t r[32];
       tc::tmem_ld_x32(tlane + col0 + 32u * t, r);
       const int f0 = fout(h, 32 * t);
       float v[32];
+      if (gbias) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 bq = *reinterpret_cast<const float4*>(bias + f0 + j);
-        v[j] = bq.x; v[j + 1] = bq.y; v[j + 2] = bq.z; v[j + 3] = bq.w;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bq = *reinterpret_cast<const float4*>(gbias + f0 + j);
+          v[j] = bq.x; v[j + 1] = bq.y; v[j + 2] = bq.z; v[j + 3] = bq.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = sp.v[sx][sb_off + f0 + j];
       }
-      const int gs = eg;           // gather slice t lives in ring slot t % NG == this group's parity
+      const int gs = t & (NG - 1);           // gather slice t lives in ring slot t % NG (= this group's parity)
       if (gather) {
-        TIMED_WAIT(5, tc::mbar_wait(&s.gfull[gs], gseq & 1));
+        WAIT(&s.gfull[gs], gseq & 1);
         const float* gp = s.g[gs] + (h * 32) * G_LD + p;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += gp[j * G_LD];
         ++gseq;
       }
-      if (ew == 0) TL(tit, tli + 1);
       tc::tmem_ld_wait();
-      if (ew == 0) TL(tit, tli + 2);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + v[j], 0.f);
-      // the slot is only needed now: its release (MMA consumption of slice seq-NX) overlaps the work above
-      TIMED_WAIT(3, tc::mbar_wait(&s.xempty[slot], ((seq / NX) & 1) ^ 1));
-      if (ew == 0) TL(tit, tli + 3);
-      store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, sc_lo, sc_hi);
+      WAIT(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
+      store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, sc_lo, sc_hi, amax);
       arrive_xfull(slot);
-      if (ew == 0) TL(tit, tli + 4);
-      if (gather && lane == 0) tc::mbar_arrive(&s.gempty[gs]);   // after the critical-path signal
+      if (gather && lane == 0) tc::mbar_arrive(&s.gempty[gs]);
+    };
+    auto drain_x3 = [&](int sn) {
+      const int sx = sn & 1;
+      for (int t = eg; t < 4; t += 2)
+        drain(acc_col(0, sx), t, sx, SB_B2, nullptr, ring_seq(sn, 3, t, nstreams), false, job.act_scale[sx][1][0],
+              job.act_scale[sx][1][1], t == eg ? &s.acc_full[0][0] : nullptr, (uint32_t)sn & 1);
     };
 
-    // Per stream n (running index, parity = stream kind and TMEM mirror): X3 <- acc2, X4 <- acc3, X5 <- acc4, final <- acc5.
-    // The MMA warp issues L0(n+1) before L3(n), so acc2 of the next stream is complete early: its X3 slices are produced
-    // BEFORE this stream's final layer, and L1(n+1) can follow L3(n) on the tensor pipe without waiting for a drain.
-    const int nstreams = 2 * my_tiles;
-    auto drain_x3 = [&](int sn) {
-      const int sidx = sn & 1;
-      const float* sb = s.sb[sidx];
-      const uint32_t seq0 = (uint32_t)sn * XSLOTS_PER_STREAM, par = (uint32_t)sn & 1;
-      for (int t = eg; t < 4; t += 2)
-        drain(acc_col(0, sidx), t, sb + SB_B2, seq0 + t, false, job.act_scale[sidx][1][0], job.act_scale[sidx][1][1],
-              t == eg ? &s.acc_full[0][0] : nullptr, par);
-    };
-    if (nstreams > 0) drain_x3(0);
+    // ring order: X2_0, then per stream n: X3_n (4), X4_n (8), X2_{n+1}, X5_n (8); X3_{n+1} before stream n's final layer
+    if (nstreams > 0) {
+      if (eg == 0) stage_first(0);
+      drain_x3(0);
+    }
     for (int sn = 0; sn < nstreams; ++sn) {
       const int sidx = sn & 1, it = sn >> 1;
       const TileCoord tc0 = tile_coord((int64_t)pair + (int64_t)it * num_pairs, tiles_per_img);
-      {
-        const float* sb = s.sb[sidx];
-        const uint32_t seq0 = (uint32_t)sn * XSLOTS_PER_STREAM;
-        const uint32_t par = (uint32_t)sn & 1;
-        // fold1/conv3 output (512) -> X4
-        for (int t = eg; t < 8; t += 2)      // thread-columns [0,128) belong to N-block 0, [128,256) to N-block 1
-          drain(acc_col(1, sidx), t, sb + SB_B3, seq0 + 4 + t, false, job.act_scale[sidx][2][0], job.act_scale[sidx][2][1],
-                t == eg ? &s.acc_full[1][0] : (t == eg + 4 ? &s.acc_full[1][1] : nullptr), par);
-        // fold2/conv1 output (512) + folded image features -> X5
-        const float* b4 = sidx ? (sb + SB_B4) : (job.gbias + (int64_t)tc0.b * kHidden);
-        for (int t = eg; t < 8; t += 2)
-          drain(acc_col(2, sidx), t, b4, seq0 + 12 + t, sidx == 1, job.act_scale[sidx][3][0], job.act_scale[sidx][3][1],
-                t == eg ? &s.acc_full[2][0] : (t == eg + 4 ? &s.acc_full[2][1] : nullptr), par);
-        // next stream: fold1/conv2 output (256) -> X3 (its accumulator was filled before this stream's last layer)
-        if (sn + 1 < nstreams) drain_x3(sn + 1);
-        // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
-        TIMED_WAIT(4, tc::mbar_wait(&s.acc_full[3][0], par));
-        tc::tc_fence_after_sync();
-        if (ew == 0) TL(it, 400 + sidx * 8 + eg * 4);
-        float part = 0.f;
-        for (int t = 2 * eg; t < 2 * eg + 2; ++t) {
-          uint32_t r[32];
-          tc::tmem_ld_x32(tlane + acc_col(3, sidx) + 32u * t, r);
-          const int f0 = fout(h, 32 * t);
-          tc::tmem_ld_wait();
+      const uint32_t par = (uint32_t)sn & 1;
+      for (int t = eg; t < 8; t += 2)
+        drain(acc_col(1, sidx), t, sidx, SB_B3, nullptr, ring_seq(sn, 4, t, nstreams), false, job.act_scale[sidx][2][0],
+              job.act_scale[sidx][2][1], t == eg ? &s.acc_full[1][0] : (t == eg + 4 ? &s.acc_full[1][1] : nullptr), par);
+      if (eg == 0 && sn + 1 < nstreams) stage_first(sn + 1);
+      const float* gb = sidx ? nullptr : (job.gbias + (int64_t)tc0.b * kHidden);
+      for (int t = eg; t < 8; t += 2)
+        drain(acc_col(2, sidx), t, sidx, SB_B4, gb, ring_seq(sn, 5, t, nstreams), sidx == 1, job.act_scale[sidx][3][0],
+              job.act_scale[sidx][3][1], t == eg ? &s.acc_full[2][0] : (t == eg + 4 ? &s.acc_full[2][1] : nullptr), par);
+      if (sn + 1 < nstreams) drain_x3(sn + 1);
+      // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
+      WAIT(&s.acc_full[3][0], par);
+      tc::tc_fence_after_sync();
+      float part = 0.f;
+      for (int t = 2 * eg; t < 2 * eg + 2; ++t) {
+        uint32_t r[32];
+        tc::tmem_ld_x32(tlane + acc_col(3, sidx) + 32u * t, r);
+        const int f0 = fout(h, 32 * t);
+        tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = fmaxf(__uint_as_float(r[j]) + sb[SB_B5 + f0 + j], 0.f);
-            part = fmaf(a, sb[SB_W6 + f0 + j], part);
-          }
+        for (int j = 0; j < 32; ++j) {
+          float a = fmaxf(__uint_as_float(r[j]) + sp.v[sidx][SB_B5 + f0 + j], 0.f);
+          part = fmaf(a, sp.v[sidx][SB_W6 + f0 + j], part);
         }
-        tc::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) {
-          if (cta == 0) tc::mbar_arrive(&s.acc5_free);
-          else tc::mbar_arrive_cluster(&s.acc5_free, 0);
-        }
-        s.part[it & 1][sidx][h][eg][p] = part;
-        if (ew == 0) TL(it, 400 + sidx * 8 + eg * 4 + 1);
       }
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta == 0) tc::mbar_arrive(&s.acc5_free);
+        else tc::mbar_arrive_cluster(&s.acc5_free, 0);
+      }
+      s.part[it & 1][sidx][h][eg][p] = part;
       if (sidx == 0) continue;
       named_bar_sync(1, 256);
       if (h == 0 && eg == 0) {
@@ -407,46 +393,20 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
           float rl = ((pp[1][0][0][p] + pp[1][0][1][p]) + (pp[1][1][0][p] + pp[1][1][1][p])) + __ldg(job.l.b6);
           float r = rg + rl;
           if (job.tanh_out) r = tanhf(r);
-          job.out_pred[(int64_t)tc0.b * job.N + n] = r * job.out_scale;
+          job.out_pred[(int64_t)tc0.b * job.N + n] = __fdiv_rn(r, job.out_div);
         }
       }
     }
-    if (kTrace && tid == 128) {
-      unsigned long long* o = dbg + (size_t)blockIdx.x * 24;
-      if (cta == 1) o[4] = (unsigned long long)(clock64() - t_role0);
-      o[5] = wt[3]; o[6] = wt[4]; o[7] = wt[5];
+    if constexpr (kMode == MODE_F16F8) {
+      // fp16 range guard: +inf here means an activation exceeded 65504 and the result is meaningless
+      if ((__hisinf(__low2half(amax)) || __hisinf(__high2half(amax))) && job.status) atomicOr(job.status, DISN_STATUS_FP16_OVERFLOW);
     }
   } else if (warp >= 12) {
-    // ===================== front end: points, projection, layer 1, feature gather =====================
+    // ===================== front end: points, projection, taps (published per tile), feature gather =====================
     const int ft = tid - 384;
-    const int p = ft & 63, h = ft >> 6;
     const int fw = warp - 12;
     const int Wm = job.img_w, Hm = job.img_h;
 
-    auto stage_x2 = [&](const float* sb, uint32_t use, float sc_lo, float sc_hi) {   // use = running stream count
-      const int pb = (use >> 1) & 1;                       // tile parity of the point buffers
-      tc::mbar_wait(&s.x2empty, (use & 1) ^ 1);
-      const float x = s.px[pb][p], y = s.py[pb][p], z = s.pz[pb][p];
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int f = h * 32 + j;
-        float a = sb[SB_B1 + f];
-        a = fmaf(x, sb[SB_W1 + f], a);
-        a = fmaf(y, sb[SB_W1 + 64 + f], a);
-        a = fmaf(z, sb[SB_W1 + 128 + f], a);
-        v[j] = fmaxf(a, 0.f);
-      }
-      store_slice<kMode>(s.x2[0], s.x2[1], p, h, v, sc_lo, sc_hi);
-      tc::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (cta == 0) tc::mbar_arrive(&s.x2full);
-        else tc::mbar_arrive_cluster(&s.x2full, 0);
-      }
-    };
-
-    // query points, projection and bilinear taps of tile `it` -> parity buffers
     auto compute_points = [&](int it) {
       const TileCoord tc0 = tile_coord((int64_t)pair + (int64_t)it * num_pairs, tiles_per_img);
       const int b = tc0.b;
@@ -485,7 +445,6 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
           float* o = job.out_uv + ((int64_t)b * job.N + n) * 2;
           o[0] = u; o[1] = v;
         }
-        // tf.contrib.resampler taps (zero outside the map, whole sample zero unless -1<x<W, -1<y<H)
         int off[4] = {-1, -1, -1, -1};
         float wg[4] = {0.f, 0.f, 0.f, 0.f};
         if (u > -1.f && v > -1.f && u < (float)Wm && v < (float)Hm) {
@@ -505,29 +464,19 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         for (int k = 0; k < 4; ++k) { s.tap_off[pb][ft][k] = off[k]; s.tap_w[pb][ft][k] = wg[k]; }
       }
       named_bar_sync(2, 128);
+      if (ft == 0) tc::mbar_arrive(&s.pfull[pb]);      // epilogue group 0 computes fold1/conv1 from these points
     };
 
-    // fold1/conv1 of a stream is staged one stream ahead of the MMAs (the MMA warp issues L0(n+1) before L3(n)), so the
-    // next tile's points are computed before this tile's gather
-    if (my_tiles > 0) {
-      compute_points(0);
-      stage_x2(s.sb[0], 0u, job.act_scale[0][0][0], job.act_scale[0][0][1]);
-    }
+    // the next tile's points are published before this tile's gather: the epilogue stages stream n+1's first slice while
+    // stream n is still in its last layers
+    if (my_tiles > 0) compute_points(0);
     for (int it = 0; it < my_tiles; ++it) {
       const TileCoord tc0 = tile_coord((int64_t)pair + (int64_t)it * num_pairs, tiles_per_img);
       const int b = tc0.b;
       const int pb = it & 1;
-      stage_x2(s.sb[1], (uint32_t)it * 2 + 1, job.act_scale[1][0][0], job.act_scale[1][0][1]);
-      if (it + 1 < my_tiles) {
-        compute_points(it + 1);
-        stage_x2(s.sb[0], (uint32_t)it * 2 + 2, job.act_scale[0][0][0], job.act_scale[0][0][1]);
-      }
-      // gather of the projected feature map for the local stream's fold2/conv1 epilogue
+      if (it + 1 < my_tiles) compute_points(it + 1);
       const float* pm = job.pmap + (int64_t)b * Hm * Wm * kHidden;
       const int grp = lane >> 3, q = lane & 7;
-      // The gather is latency bound (first touch of every 128-byte tap line misses L1).  In grid mode neighbouring points
-      // share taps, so one slice's lines fit the small L1 next to the 217 KB of shared memory: while slice t is gathered,
-      // slice t+1's lines are prefetched (one lane per line: 16 points x 4 taps x 2 halves per warp).  Hint only.
       const bool pf = (job.pts == nullptr);
       auto prefetch_slice = [&](int t) {
         const int ppt = fw * 16 + (lane >> 1), phh = lane & 1;
@@ -542,7 +491,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
         const uint32_t gsq = (uint32_t)it * 8 + t;
         const int gs = gsq % NG;
         if (pf && t + 1 < 8) prefetch_slice(t + 1);
-        tc::mbar_wait(&s.gempty[gs], ((gsq / NG) & 1) ^ 1);
+        WAIT(&s.gempty[gs], ((gsq / NG) & 1) ^ 1);
         float* gdst = s.g[gs];
 #pragma unroll
         for (int i2 = 0; i2 < 4; i2 += 2) {       // two point groups at a time: 16 x 16 B loads in flight per lane
@@ -586,6 +535,7 @@ point_tc_kernel(PointJob job, const uint8_t* __restrict__ wpk, int64_t tiles_per
   // ---- teardown ----
   tc::tc_fence_before_sync();
   tc::cluster_sync();
+  if ((kVar & 1) && dbg && threadIdx.x == 0) dbg[blockIdx.x] = (unsigned long long)(clock64() - t_start);
   if (warp == 2) tc::tmem_dealloc_cg2(tmem, 512);
 }
 
@@ -594,6 +544,38 @@ inline int fin_of(int layer, int t, int k) {
   if (layer == 0) return k;                           // X2 is written in natural order
   const int c = 32 * t + (k % 32);
   return fout(k / 32, c);
+}
+
+template <int kMode, int kVar>
+int launch_var(disn_ctx* c, const PointJob& job, const SmallParams& sp, const void* wpk, int pairs, int smem,
+               int64_t tiles_per_img) {
+  // the attribute belongs to (function, device): remembered per context, not per process (a second engine on another
+  // device in the same process would otherwise launch with the 48 KB default)
+  bool& attr = c->attr_point_tc[kMode * 2 + (kVar & 1)];
+  if (!attr) {
+    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<kMode, kVar>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  unsigned long long* dbg = nullptr;
+  int expt = 0;
+  if constexpr ((kVar & 1) != 0) {
+    expt = getenv("DISN_TC_EXPT") ? atoi(getenv("DISN_TC_EXPT")) : 0;
+    DISN_CUDA_OK(cudaMalloc(&dbg, (size_t)pairs * 2 * sizeof(unsigned long long)));
+  }
+  point_tc_kernel<kMode, kVar><<<pairs * 2, NTHREADS, smem, c->stream>>>(job, sp, reinterpret_cast<const uint8_t*>(wpk),
+                                                                        tiles_per_img, dbg, expt);
+  if constexpr ((kVar & 1) != 0) {
+    std::vector<unsigned long long> h((size_t)pairs * 2);
+    DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+    DISN_CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    double sum = 0, mx = 0;
+    for (auto v : h) { sum += (double)v; mx = std::max(mx, (double)v); }
+    const double tiles = (double)(tiles_per_img * job.B) / pairs;
+    fprintf(stderr, "[DISN_TC_MEASURE expt=%d] CTA cycles: mean %.0f max %.0f  -> %.1f Kcycles per tile (%.1f tiles per pair)\n",
+            expt, sum / h.size(), mx, sum / h.size() / tiles / 1000.0, tiles);
+  }
+  return 0;
 }
 
 }  // namespace
@@ -694,7 +676,7 @@ int tc_pack_weights(disn_ctx* c) {
   DISN_CUDA_OK(cudaMemcpyAsync(c->tc_weights_f8, img.data(), total, cudaMemcpyHostToDevice, c->stream));
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
 
-  // host copy of the small per-stream parameters at the SB_* offsets (parameter table of the experimental v2 kernel)
+  // host copy of the small per-stream parameters at the SB_* offsets (the kernel's __grid_constant__ parameter table)
   c->tc_small_ok = true;
   for (int sidx = 0; sidx < 2; ++sidx) {
     const std::string p = sidx ? "sdfprediction_imgfeat" : "sdfprediction";
@@ -704,10 +686,7 @@ int tc_pack_weights(disn_ctx* c) {
         {"/fold1/conv1/biases", SB_B1, 64}};
     for (const auto& e : small) {
       auto it = c->weights.find(p + e.name);
-      if (it == c->weights.end() || it->second.numel != e.n) {   // never fatal here: only the experimental kernel needs it
-        c->tc_small_ok = false;
-        continue;
-      }
+      DISN_REQUIRE(it != c->weights.end() && it->second.numel == e.n, "missing or mis-shaped variable " + p + e.name);
       DISN_CUDA_OK(cudaMemcpyAsync(&c->tc_small[sidx][e.off], it->second.ptr, (size_t)e.n * sizeof(float),
                                    cudaMemcpyDeviceToHost, c->stream));
     }
@@ -716,84 +695,29 @@ int tc_pack_weights(disn_ctx* c) {
   return 0;
 }
 
-template <bool kTrace, int kMode>
-static int launch_variant(disn_ctx* c, const PointJob& job, const void* wpk, int pairs, int smem, int64_t tiles_per_img,
-                          unsigned long long* dbg) {
-  const int expt = getenv("DISN_TC_EXPT") ? atoi(getenv("DISN_TC_EXPT")) : 0;   // trace build only: skip MMA groups
-  static bool attr_set = false;
-  if (!attr_set) {
-    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<kTrace, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  point_tc_kernel<kTrace, kMode><<<pairs * 2, NTHREADS, smem, c->stream>>>(job, reinterpret_cast<const uint8_t*>(wpk),
-                                                                          tiles_per_img, dbg, expt);
-  return 0;
-}
-
 int launch_point_tc(disn_ctx* c, const PointJob& job_in) {
-  if (const char* v2 = getenv("DISN_TC_V2")) {      // experimental kernel revision, see point_tc_v2.cu
-    if (v2[0] == '1') return launch_point_tc_v2(c, job_in);
-  }
   const bool f8 = c->cfg.precision == DISN_PREC_F16F8;
   const void* wpk = f8 ? c->tc_weights_f8 : c->tc_weights;
   DISN_REQUIRE(wpk != nullptr, "tensor-core weights not packed (call disn_finalize_weights)");
+  static_assert(sizeof(SmallParams) == sizeof(c->tc_small), "small-parameter table layout");
   PointJob job = job_in;
   memcpy(job.act_scale, c->tc_act_scale, sizeof(job.act_scale));
+  SmallParams sp;
+  memcpy(&sp, c->tc_small, sizeof(sp));
   const int smem = (int)sizeof(TcSmem) + 1024;
   const int64_t tiles_per_img = (job.N + 2 * PTS - 1) / (2 * PTS);
   const int64_t total = tiles_per_img * job.B;
   if (total == 0) return 0;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
-  int pairs = (int)std::min<int64_t>(total, sms / 2);
-  unsigned long long* dbg = nullptr;
-  const bool trace = getenv("DISN_TC_TRACE") != nullptr;
-  if (trace) {
-    DISN_CUDA_OK(cudaMalloc(&dbg, ((size_t)pairs * 2 * 24 + 512) * sizeof(unsigned long long)));
-    DISN_CUDA_OK(cudaMemsetAsync(dbg, 0, ((size_t)pairs * 2 * 24 + 512) * sizeof(unsigned long long), c->stream));
-  }
+  const int pairs = (int)std::min<int64_t>(total, c->num_sms / 2);
+  const bool measure = getenv("DISN_TC_MEASURE") != nullptr;
   int rc;
-  if (trace) rc = f8 ? launch_variant<true, MODE_F16F8>(c, job, wpk, pairs, smem, tiles_per_img, dbg)
-                     : launch_variant<true, MODE_BF16X3>(c, job, wpk, pairs, smem, tiles_per_img, dbg);
-  else rc = f8 ? launch_variant<false, MODE_F16F8>(c, job, wpk, pairs, smem, tiles_per_img, dbg)
-               : launch_variant<false, MODE_BF16X3>(c, job, wpk, pairs, smem, tiles_per_img, dbg);
+  if (measure) rc = f8 ? launch_var<MODE_F16F8, 1>(c, job, sp, wpk, pairs, smem, tiles_per_img)
+                       : launch_var<MODE_BF16X3, 1>(c, job, sp, wpk, pairs, smem, tiles_per_img);
+  else rc = f8 ? launch_var<MODE_F16F8, 0>(c, job, sp, wpk, pairs, smem, tiles_per_img)
+               : launch_var<MODE_BF16X3, 0>(c, job, sp, wpk, pairs, smem, tiles_per_img);
   if (rc) return rc;
   c->launches++;
   DISN_CUDA_OK(cudaGetLastError());
-  if (trace) {   // debug only: per-role blocked cycles, averaged over CTAs
-    std::vector<unsigned long long> h((size_t)pairs * 2 * 24 + 512);
-    DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
-    DISN_CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    cudaFree(dbg);
-    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = 0; p < pairs; ++p) {
-      for (int k = 0; k < 4; ++k) a[k] += (double)h[(size_t)(2 * p) * 24 + k] / pairs;                 // leader's MMA warp
-      a[4] += (double)h[(size_t)(2 * p + 1) * 24 + 4] / pairs;                                          // peer epilogue total
-      for (int k = 5; k < 8; ++k) a[k] += 0.5 * ((double)h[(size_t)(2 * p) * 24 + k] + (double)h[(size_t)(2 * p + 1) * 24 + k]) / pairs;
-    }
-    const double tiles = (double)total / pairs;
-    fprintf(stderr, "[DISN_TC_TRACE] tiles/pair=%.1f  per-tile cycles: MMA warp total=%.0f wait{weights=%.0f, act=%.0f, acc5=%.0f} | "
-                    "epilogue warp total=%.0f wait{xempty=%.0f, acc_full=%.0f, gather=%.0f}\n",
-            tiles, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles, a[6] / tiles, a[7] / tiles);
-    if (const char* tlf = getenv("DISN_TC_TIMELINE")) {     // raw stamps of tile 4 of CTA 0
-      if (FILE* f = fopen(tlf, "w")) {
-        for (int i = 0; i < 512; ++i) fprintf(f, "%d %llu\n", i, h[(size_t)pairs * 2 * 24 + i]);
-        fclose(f);
-      }
-    }
-    double lw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = 0; p < pairs; ++p)
-      for (int k = 0; k < 8; ++k) lw[k] += (double)h[(size_t)(2 * p) * 24 + 8 + k] / pairs / tiles;
-    double issue = 0;
-    for (int p = 0; p < pairs; ++p) issue += (double)h[(size_t)(2 * p) * 24 + 4] / pairs / tiles;
-    double cx = 0, ca = 0;
-    for (int p = 0; p < pairs; ++p) { cx += (double)h[(size_t)(2 * p) * 24 + 16] / pairs / tiles; ca += (double)h[(size_t)(2 * p) * 24 + 17] / pairs / tiles; }
-    fprintf(stderr, "[DISN_TC_TRACE] MMA warp per tile: MMA issue + commit blocks (66) = %.0f cycles\n", issue);
-    (void)cx;
-    (void)ca;
-    fprintf(stderr, "[DISN_TC_TRACE] MMA warp activation waits per tile: global L2..L5 = %.0f %.0f %.0f %.0f | local L2..L5 = %.0f %.0f %.0f %.0f\n",
-            lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
-  }
   return 0;
 }
 

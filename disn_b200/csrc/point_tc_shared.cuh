@@ -1,5 +1,5 @@
-// Pieces shared by the tensor-core point kernels (point_tc.cu and the experimental point_tc_v2.cu): tile geometry,
-// accumulator column maps, operand-split stores.  Included inside namespace disn { namespace { ... } }.
+// Pieces of the tensor-core point kernel (point_tc.cu) that are also host-visible: tile geometry, accumulator
+// column maps, operand-split stores.  Included inside namespace disn { namespace { ... } }.
 #pragma once
 
 constexpr int NX = 3;                 // activation (A operand) ring slots
@@ -49,9 +49,11 @@ constexpr int W8_TILE = 8192;    // 128 rows x 64 k x 1 B (SW64)
 // write one thread's 32 consecutive K values of row p into an A-tile slot.
 // MODE_BF16X3: x0 = bf16 hi tile, x1 = bf16 lo tile (both SW128).
 // MODE_F16F8 : x0 = fp16 tile (SW128), x1 = [e5m2((a-h).sc_lo) | e5m2(a.sc_hi)] two SW64 byte tiles.
+// MODE_F16F8 also folds the slice's fp16 values into `amax` (all values are post-ReLU, i.e. >= 0): an activation above
+// fp16's 65504 becomes +inf there, which the kernel reports through PointJob::status instead of producing a silent inf.
 template <int kMode>
 __device__ __forceinline__ void store_slice(uint8_t* x0, uint8_t* x1, int p, int h, const float* v, float sc_lo,
-                                            float sc_hi) {
+                                            float sc_hi, __half2& amax) {
   if constexpr (kMode == MODE_BF16X3) {
     uint32_t hi[16], lo[16];
 #pragma unroll
@@ -69,6 +71,7 @@ __device__ __forceinline__ void store_slice(uint8_t* x0, uint8_t* x1, int p, int
     for (int j = 0; j < 16; ++j) {
       const float a = v[2 * j], b = v[2 * j + 1];
       const __half2 hh = __floats2half2_rn(a, b);
+      amax = __hmax2(amax, hh);
       m[j] = *reinterpret_cast<const uint32_t*>(&hh);
       const float ra = a - __low2float(hh), rb = b - __high2float(hh);
       const uint32_t l = __nv_cvt_float2_to_fp8x2(make_float2(ra * sc_lo, rb * sc_lo), __NV_SATFINITE, __NV_E5M2);

@@ -106,7 +106,7 @@ def test_grid_equals_explicit_points_bitwise(engine, he_weights):
     pts = orc.grid_points(sp[0], res + 1)[None]
     by_pts = engine.eval_points(pts, tm) / np.float32(orc.SDF_WEIGHT)
     by_grid = engine.eval_grid(sp, tm, res)
-    np.testing.assert_allclose(by_grid.reshape(-1), by_pts.reshape(-1), rtol=0, atol=1e-7)
+    np.testing.assert_array_equal(by_grid.reshape(-1), by_pts.reshape(-1))
 
 
 def test_xavier_reference_init_and_224_input(engine, he_weights):

@@ -9,11 +9,11 @@ from disn_b200 import synth
 from disn_b200.engine import Engine
 
 W = synth.make_weights(seed=7, init="he")
-for prec in ("fp32", "bf16x3"):
+for prec in (sys.argv[1:] or ["fp32", "bf16x3", "f16f8"]):
     eng = Engine(device=0, precision=prec)
     eng.load_weights(W)
     eng.encode(synth.synthetic_images(1))
-    pts = np.random.default_rng(0).uniform(-1, 1, (1, 300, 3)).astype(np.float32)
+    pts = np.random.default_rng(0).uniform(-1, 1, (1, 300, 3)).astype(np.float32)   # 3 pair-tiles: ring wrap-around, tail tile
     out = eng.eval_points(pts, synth.DEMO_TRANS_MAT)
     g = eng.eval_grid(synth.DEMO_SDF_PARAMS, synth.DEMO_TRANS_MAT, 6)
     v, f = eng.marching_cubes(g[0], [-1, -1, -1, 1, 1, 1], float(np.median(g)))
