@@ -50,6 +50,24 @@ EXPORTS = {
                                       C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int64),
                                       C.c_uint32]),
     "disn_launch_count": (C.c_int64, [C.c_void_p]),
+    "disn_eval_grid_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_int32, C.c_int32,
+                                          C.POINTER(C.c_void_p)]),
+    "disn_mc_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_float, C.c_uint32,
+                              C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "disn_mc_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "disn_mc_write_obj": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "disn_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "disn_iou": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                           C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
+    "disn_eval_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_uint32]),
+    "disn_eval_points_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "disn_point_img_feat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+}
+
+# diagnostics (include/disn_b200_test.h), exported by libdisn_b200_test.so only
+TEST_EXPORTS = {
     "disn_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "disn_tc_stream_probe": (C.c_int, [C.c_int]),
@@ -60,6 +78,9 @@ EXPORTS = {
 }
 
 _lib = None
+_test_lib = None
+TEST_LIB_PATH = os.path.join(HERE, "libdisn_b200_test.so")
+
 
 
 def load(build_if_missing: bool = True):
@@ -80,6 +101,24 @@ def load(build_if_missing: bool = True):
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    return lib
+
+
+def load_test():
+    """The diagnostics library (selftests, probes, debug GEMM harness) -- tests/ and tools/ only."""
+    global _test_lib
+    if _test_lib is not None:
+        return _test_lib
+    load()
+    if not os.path.exists(TEST_LIB_PATH):
+        raise RuntimeError("libdisn_b200_test.so is missing: build it with `python -m disn_b200.build`")
+    lib = C.CDLL(TEST_LIB_PATH)
+    for table in (EXPORTS, TEST_EXPORTS):
+        for name, (res, args) in table.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    _test_lib = lib
     return lib
 
 

@@ -113,53 +113,50 @@ def build_grid_points(sdf_params_b):
     return np.stack([x, y, z], axis=3).astype(np.float32).reshape(1, -1, 3)
 
 
-def test_one_epoch(sess, ops, batches, fused=True):
-    """test/create_sdf.py:224-289.  fused=True evaluates the dense grid with one ``disn_eval_grid`` call
-    (grid generated on the device); fused=False replays the reference's loop literally -- host grid,
-    SPLIT_SIZE chunks of NUM_SAMPLE_POINTS through ``sess.run``, reassembly, /SDF_WEIGHT."""
-    is_training = False
+def obj_path(dir, cat_id, obj_nm, view_id):
+    """file naming of create_obj (test/create_sdf.py:305-312)"""
+    if not isinstance(view_id, str):
+        view_id = "%02d" % view_id
+    dir = os.path.join(dir, cat_id)
+    os.makedirs(dir, exist_ok=True)
+    return os.path.join(dir, cat_id + "_" + obj_nm + "_" + view_id + ".obj")
+
+
+def test_one_epoch(sess, ops, batches):
+    """test/create_sdf.py:224-289 on the device: per batch one encode + one dense-grid evaluation that STAYS in HBM
+    (disn_eval_grid_resident), then per image the CUDA marching-cubes post-pass straight on that buffer and the OBJ writer
+    (formatted on a worker thread, like the reference's 4-worker pool for its mesher, create_sdf.py:238,288).
+    No .dist round trip through the file system; FLAGS.keep_dist=True also writes the reference's .dist artefact.
+    The reference's literal loop (host grid, SPLIT_SIZE chunks through sess.run, reassembly, /SDF_WEIGHT) is kept as a
+    verification aid in tests/reference_loop.py."""
     log_string(str(datetime.now()))
     written = []
+    R = RESOLUTION
     with ThreadPoolExecutor(max_workers=4) as executor:
         futures = []
         for batch_idx, batch_data in enumerate(batches):
-            if fused:
-                with _ENGINE_LOCK:
-                    sess.engine.encode(batch_data["img"])
-                    sess._img_key = None
-                    grid = sess.engine.eval_grid(batch_data["sdf_params"], batch_data["trans_mat"], FLAGS.sdf_res)
-                result = grid.reshape(BATCH_SIZE, -1, 1)
-            else:
-                extra_pts = np.zeros((1, SPLIT_SIZE * NUM_SAMPLE_POINTS - TOTAL_POINTS, 3), dtype=np.float32)
-                batch_points = np.zeros((SPLIT_SIZE, 0, NUM_SAMPLE_POINTS, 3), dtype=np.float32)
+            with _ENGINE_LOCK:
+                sess.engine.encode(batch_data["img"])
+                sess._img_key = None
+                grid_ptr = sess.engine.eval_grid_resident(batch_data["sdf_params"], batch_data["trans_mat"], FLAGS.sdf_res)
                 for b in range(BATCH_SIZE):
-                    all_pts = build_grid_points(batch_data["sdf_params"][b])
-                    all_pts = np.concatenate((all_pts, extra_pts), axis=1).reshape(SPLIT_SIZE, 1, -1, 3)
-                    batch_points = np.concatenate((batch_points, all_pts), axis=1)
-                pred_sdf_val_all = np.zeros((SPLIT_SIZE, BATCH_SIZE, NUM_SAMPLE_POINTS, 1))
-                for sp in range(SPLIT_SIZE):
-                    feed_dict = {ops["is_training_pl"]: is_training,
-                                 ops["input_pls"]["sample_pc"]: batch_points[sp, ...].reshape(BATCH_SIZE, -1, 3),
-                                 ops["input_pls"]["sample_pc_rot"]: batch_points[sp, ...].reshape(BATCH_SIZE, -1, 3),
-                                 ops["input_pls"]["imgs"]: batch_data["img"],
-                                 ops["input_pls"]["trans_mat"]: batch_data["trans_mat"]}
-                    output_list = [ops["end_points"]["pred_sdf"], ops["end_points"]["ref_img"],
-                                   ops["end_points"]["sample_img_points"]]
-                    with _ENGINE_LOCK:
-                        pred_sdf_val, ref_img_val, sample_img_points_val = sess.run(output_list, feed_dict=feed_dict)
-                    pred_sdf_val_all[sp, :, :, :] = pred_sdf_val
-                pred_sdf_val_all = np.swapaxes(pred_sdf_val_all, 0, 1)
-                pred_sdf_val_all = pred_sdf_val_all.reshape((BATCH_SIZE, -1, 1))[:, :TOTAL_POINTS, :]
-                result = pred_sdf_val_all / SDF_WEIGHT
-            for b in range(BATCH_SIZE):
-                print("{}/{}, submit create_obj {}, {}, {}".format(batch_idx, "?", batch_data["cat_id"][b],
-                                                                   batch_data["obj_nm"][b], batch_data["view_id"][b]))
-                futures.append(executor.submit(create_obj, result[b], batch_data["sdf_params"][b], RESULT_OBJ_PATH,
-                                               batch_data["cat_id"][b], batch_data["obj_nm"][b],
-                                               batch_data["view_id"][b], FLAGS.iso))
+                    print("{}/{}, submit create_obj {}, {}, {}".format(batch_idx, "?", batch_data["cat_id"][b],
+                                                                       batch_data["obj_nm"][b], batch_data["view_id"][b]))
+                    path = obj_path(RESULT_OBJ_PATH, batch_data["cat_id"][b], batch_data["obj_nm"][b], batch_data["view_id"][b])
+                    dev = grid_ptr + b * R * R * R * 4
+                    verts, faces = sess.engine.marching_cubes(None, batch_data["sdf_params"][b], float(FLAGS.iso),
+                                                              device_ptr=dev, R=R)
+                    if getattr(FLAGS, "keep_dist", False):
+                        to_binary(R - 1, batch_data["sdf_params"][b], sess.engine.fetch(dev, (R, R, R)), path[:-4] + ".dist")
+                    futures.append(executor.submit(_write_and_return, path, verts, faces))
         for f in futures:
             written.append(f.result())
     return written
+
+
+def _write_and_return(path, verts, faces):
+    write_obj(path, verts, faces)
+    return path
 
 
 def to_binary(res, pos, pred_sdf_val_all, sdf_file):
@@ -170,13 +167,8 @@ def to_binary(res, pos, pred_sdf_val_all, sdf_file):
 
 def create_obj(pred_sdf_val, sdf_params, dir, cat_id, obj_nm, view_id, i):
     """test/create_sdf.py:305-317."""
-    if not isinstance(view_id, str):
-        view_id = "%02d" % view_id
-    dir = os.path.join(dir, cat_id)
-    os.makedirs(dir, exist_ok=True)
-    obj_nm = cat_id + "_" + obj_nm
-    cube_obj_file = os.path.join(dir, obj_nm + "_" + view_id + ".obj")
-    sdf_file = os.path.join(dir, obj_nm + "_" + view_id + ".dist")
+    cube_obj_file = obj_path(dir, cat_id, obj_nm, view_id)
+    sdf_file = cube_obj_file[:-4] + ".dist"
     to_binary((RESOLUTION - 1), sdf_params, pred_sdf_val, sdf_file)
     create_one_cube_obj("./isosurface/computeMarchingCubes", i, sdf_file, cube_obj_file)
     if os.path.exists(sdf_file):

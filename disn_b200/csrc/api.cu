@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -74,6 +75,11 @@ void disn_destroy(disn_ctx* c) {
   if (c->tc_weights) cudaFree(c->tc_weights);
   if (c->tc_weights_f8) cudaFree(c->tc_weights_f8);
   if (c->d_status) cudaFree(c->d_status);
+  mc_free(c);
+  if (c->d_grid) cudaFree(c->d_grid);
+  if (c->d_mc_in) cudaFree(c->d_mc_in);
+  if (c->nn_scratch) cudaFree(c->nn_scratch);
+  if (c->dec_scratch) cudaFree(c->dec_scratch);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -224,7 +230,8 @@ static void fill_stream(disn_ctx* c, const std::string& p, StreamWeights& s) {
   s.w6 = W(c, p + "/fold2/conv5/weights"); s.b6 = W(c, p + "/fold2/conv5/biases");
 }
 
-static int ensure_scratch(disn_ctx* c, int64_t pts) {
+}  // extern "C"
+int disn::ensure_point_scratch(disn_ctx* c, int64_t pts) {
   if (pts <= c->scratch_pts) return 0;
   for (float** p : {&c->d_pts, &c->d_pts_rot, &c->d_out, &c->d_uv}) { if (*p) cudaFree(*p); *p = nullptr; }
   DISN_CUDA_OK(cudaMalloc(&c->d_pts, pts * 3 * sizeof(float)));
@@ -245,9 +252,9 @@ static float* pinned_alias(const void* p) {
   return nullptr;
 }
 
-static int run_job(disn_ctx* c, PointJob& job) {
-  job.gbias = c->gbias;
-  job.pmap = c->pmap;
+int disn::run_point_job(disn_ctx* c, PointJob& job) {
+  if (!job.gbias) job.gbias = c->gbias;
+  if (!job.pmap) job.pmap = c->pmap;
   job.img_h = c->cfg.img_h; job.img_w = c->cfg.img_w;
   job.clamp_max = c->cfg.clamp_max;
   job.tanh_out = c->cfg.tanh_out;
@@ -260,6 +267,8 @@ static int run_job(disn_ctx* c, PointJob& job) {
   DISN_CUDA_OK(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   return 0;
 }
+
+extern "C" {
 
 int disn_eval_points(disn_ctx* c, const float* pts, const float* pts_rot, const float* trans_mat, int32_t B,
                      int64_t N, float* out_pred, float* out_uv, uint32_t flags) {
@@ -274,9 +283,9 @@ int disn_eval_points(disn_ctx* c, const float* pts, const float* pts_rot, const 
   if (flags & DISN_DEVICE_PTR) {
     job.pts = pts; job.pts_rot = (pts_rot && pts_rot != pts) ? pts_rot : nullptr;
     job.trans_mat = trans_mat; job.out_pred = out_pred; job.out_uv = out_uv;
-    return run_job(c, job);
+    return run_point_job(c, job);
   }
-  if (ensure_scratch(c, (int64_t)B * N)) return -1;
+  if (ensure_point_scratch(c, (int64_t)B * N)) return -1;
   float* pred_alias = pinned_alias(out_pred);
   float* uv_alias = out_uv ? pinned_alias(out_uv) : nullptr;
   size_t nb = (size_t)B * N * 3 * sizeof(float);
@@ -290,7 +299,7 @@ int disn_eval_points(disn_ctx* c, const float* pts, const float* pts_rot, const 
   job.trans_mat = c->d_tm;
   job.out_pred = pred_alias ? pred_alias : c->d_out;
   job.out_uv = out_uv ? (uv_alias ? uv_alias : c->d_uv) : nullptr;
-  if (run_job(c, job)) return -1;
+  if (run_point_job(c, job)) return -1;
   if (!pred_alias)
     DISN_CUDA_OK(cudaMemcpyAsync(out_pred, c->d_out, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   if (out_uv && !uv_alias)
@@ -351,19 +360,19 @@ int disn_eval_grid(disn_ctx* c, const double* sdf_params, const float* trans_mat
   if (flags & DISN_DEVICE_PTR) {
     job.trans_mat = trans_mat;
     job.out_pred = out_sdf;
-    return run_job(c, job);
+    return run_point_job(c, job);
   }
   DISN_CUDA_OK(cudaMemcpyAsync(c->d_tm, trans_mat, (size_t)B * 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   job.trans_mat = c->d_tm;
   if (float* alias = pinned_alias(out_sdf)) {     // pinned caller buffer: the kernel writes the host grid directly
     job.out_pred = alias;
-    if (run_job(c, job)) return -1;
+    if (run_point_job(c, job)) return -1;
     DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
     return check_status(c);
   }
-  if (ensure_scratch(c, (int64_t)B * N)) return -1;
+  if (ensure_point_scratch(c, (int64_t)B * N)) return -1;
   job.out_pred = c->d_out;
-  if (run_job(c, job)) return -1;
+  if (run_point_job(c, job)) return -1;
   DISN_CUDA_OK(cudaMemcpyAsync(out_sdf, c->d_out, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
   return check_status(c);
@@ -382,6 +391,19 @@ int disn_write_dist(const char* path, int32_t res, const double* bbox, const flo
   return 0;
 }
 
+// one persistent device scratch for the small evaluators (grows, freed in disn_destroy)
+static int small_scratch(disn_ctx* c, int64_t bytes, char** out) {
+  if (bytes > c->nn_scratch_bytes) {
+    if (c->nn_scratch) cudaFree(c->nn_scratch);
+  if (c->dec_scratch) cudaFree(c->dec_scratch);
+    c->nn_scratch = nullptr; c->nn_scratch_bytes = 0;
+    DISN_CUDA_OK(cudaMalloc(&c->nn_scratch, (size_t)bytes));
+    c->nn_scratch_bytes = bytes;
+  }
+  *out = static_cast<char*>(c->nn_scratch);
+  return 0;
+}
+
 int disn_cam_estimate(disn_ctx* c, const float* imgs, int32_t B, int32_t H, int32_t W, int32_t C, const float* K,
                       float* out_rt, float* out_trans_mat) {
   DISN_REQUIRE(c && imgs && out_trans_mat, "null argument");
@@ -389,18 +411,16 @@ int disn_cam_estimate(disn_ctx* c, const float* imgs, int32_t B, int32_t H, int3
   DISN_REQUIRE(B >= 1 && B <= c->cfg.max_batch, "batch exceeds max_batch of the context");
   if (encoder_run(c, imgs, B, H, W, C, false, /*embedding_only=*/true)) return -1;
   static const float kDefaultK[9] = {149.84375f, 0.f, 68.5f, 0.f, 149.84375f, 68.5f, 0.f, 0.f, 1.f};
-  float *dK = nullptr, *dRT = nullptr, *dTM = nullptr;
-  auto cleanup = [&]() { cudaFree(dK); cudaFree(dRT); cudaFree(dTM); };
-  cudaError_t e;
-#define CAM_OK(expr) if ((e = (expr)) != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e)); cleanup(); return -1; }
-  CAM_OK(cudaMalloc(&dK, 9 * 4)); CAM_OK(cudaMalloc(&dRT, (size_t)B * 12 * 4)); CAM_OK(cudaMalloc(&dTM, (size_t)B * 12 * 4));
-  CAM_OK(cudaMemcpyAsync(dK, K ? K : kDefaultK, 9 * 4, cudaMemcpyHostToDevice, c->stream));
-  if (launch_cam_heads(c, B, dK, dRT, dTM)) { cleanup(); return -1; }
-  if (out_rt) CAM_OK(cudaMemcpyAsync(out_rt, dRT, (size_t)B * 12 * 4, cudaMemcpyDeviceToHost, c->stream));
-  CAM_OK(cudaMemcpyAsync(out_trans_mat, dTM, (size_t)B * 12 * 4, cudaMemcpyDeviceToHost, c->stream));
-  CAM_OK(cudaStreamSynchronize(c->stream));
-#undef CAM_OK
-  cleanup();
+  char* base = nullptr;
+  if (small_scratch(c, 256 + (int64_t)B * 12 * 4 * 2, &base)) return -1;
+  float* dK = reinterpret_cast<float*>(base);
+  float* dRT = reinterpret_cast<float*>(base + 256);
+  float* dTM = dRT + (size_t)B * 12;
+  DISN_CUDA_OK(cudaMemcpyAsync(dK, K ? K : kDefaultK, 9 * 4, cudaMemcpyHostToDevice, c->stream));
+  if (launch_cam_heads(c, B, dK, dRT, dTM)) return -1;
+  if (out_rt) DISN_CUDA_OK(cudaMemcpyAsync(out_rt, dRT, (size_t)B * 12 * 4, cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaMemcpyAsync(out_trans_mat, dTM, (size_t)B * 12 * 4, cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -409,24 +429,23 @@ int disn_nn_distance(disn_ctx* c, const float* xyz1, const float* xyz2, int32_t 
   DISN_REQUIRE(c && xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "null argument");
   DISN_REQUIRE(B >= 1 && N >= 1 && M >= 1, "NnDistance requires non-empty point sets of shape (batch,#points,3)");
   DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
-  float *d1 = nullptr, *d2 = nullptr, *o1 = nullptr, *o2 = nullptr;
-  int *i1 = nullptr, *i2 = nullptr;
-  auto cleanup = [&]() { cudaFree(d1); cudaFree(d2); cudaFree(o1); cudaFree(o2); cudaFree(i1); cudaFree(i2); };
-  cudaError_t e;
-#define NN_OK(expr) if ((e = (expr)) != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e)); cleanup(); return -1; }
-  NN_OK(cudaMalloc(&d1, (size_t)B * N * 3 * 4)); NN_OK(cudaMalloc(&d2, (size_t)B * M * 3 * 4));
-  NN_OK(cudaMalloc(&o1, (size_t)B * N * 4)); NN_OK(cudaMalloc(&o2, (size_t)B * M * 4));
-  NN_OK(cudaMalloc(&i1, (size_t)B * N * 4)); NN_OK(cudaMalloc(&i2, (size_t)B * M * 4));
-  NN_OK(cudaMemcpyAsync(d1, xyz1, (size_t)B * N * 3 * 4, cudaMemcpyHostToDevice, c->stream));
-  NN_OK(cudaMemcpyAsync(d2, xyz2, (size_t)B * M * 3 * 4, cudaMemcpyHostToDevice, c->stream));
-  if (nn_distance(c, d1, N, d2, M, B, o1, i1, o2, i2)) { cleanup(); return -1; }
-  NN_OK(cudaMemcpyAsync(dist1, o1, (size_t)B * N * 4, cudaMemcpyDeviceToHost, c->stream));
-  NN_OK(cudaMemcpyAsync(idx1, i1, (size_t)B * N * 4, cudaMemcpyDeviceToHost, c->stream));
-  NN_OK(cudaMemcpyAsync(dist2, o2, (size_t)B * M * 4, cudaMemcpyDeviceToHost, c->stream));
-  NN_OK(cudaMemcpyAsync(idx2, i2, (size_t)B * M * 4, cudaMemcpyDeviceToHost, c->stream));
-  NN_OK(cudaStreamSynchronize(c->stream));
-#undef NN_OK
-  cleanup();
+  const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
+  char* base = nullptr;
+  if (small_scratch(c, (int64_t)((n1 + n2) * (3 + 1 + 1) * 4 + 1024), &base)) return -1;
+  float* d1 = reinterpret_cast<float*>(base);
+  float* d2 = d1 + n1 * 3;
+  float* o1 = d2 + n2 * 3;
+  float* o2 = o1 + n1;
+  int* i1 = reinterpret_cast<int*>(o2 + n2);
+  int* i2 = i1 + n1;
+  DISN_CUDA_OK(cudaMemcpyAsync(d1, xyz1, n1 * 3 * 4, cudaMemcpyHostToDevice, c->stream));
+  DISN_CUDA_OK(cudaMemcpyAsync(d2, xyz2, n2 * 3 * 4, cudaMemcpyHostToDevice, c->stream));
+  if (nn_distance(c, d1, N, d2, M, B, o1, i1, o2, i2)) return -1;
+  DISN_CUDA_OK(cudaMemcpyAsync(dist1, o1, n1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaMemcpyAsync(idx1, i1, n1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaMemcpyAsync(dist2, o2, n2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaMemcpyAsync(idx2, i2, n2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -448,23 +467,84 @@ int disn_write_obj(const char* path, const float* verts, int64_t n_verts, const 
   return 0;
 }
 
+// staging of a host SDF grid for marching cubes (persistent, grows)
+static int mc_input(disn_ctx* c, const float* sdf, int32_t R, uint32_t flags, const float** d_sdf) {
+  if (flags & DISN_DEVICE_PTR) { *d_sdf = sdf; return 0; }
+  const int64_t n = (int64_t)R * R * R;
+  if (n > c->mc_in_cap) {
+    if (c->d_mc_in) cudaFree(c->d_mc_in);
+    c->d_mc_in = nullptr; c->mc_in_cap = 0;
+    DISN_CUDA_OK(cudaMalloc(&c->d_mc_in, (size_t)n * sizeof(float)));
+    c->mc_in_cap = n;
+  }
+  DISN_CUDA_OK(cudaMemcpyAsync(c->d_mc_in, sdf, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  *d_sdf = c->d_mc_in;
+  return 0;
+}
+
+int disn_mc_run(disn_ctx* c, const float* sdf, int32_t R, const double* bbox, float iso, uint32_t flags,
+                int64_t* n_verts, int64_t* n_faces) {
+  DISN_REQUIRE(c && sdf && bbox, "null argument");
+  DISN_REQUIRE(R >= 2, "need at least 2 samples per axis");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  const float* d_sdf = nullptr;
+  if (mc_input(c, sdf, R, flags, &d_sdf)) return -1;
+  return mc_run(c, d_sdf, R, bbox, iso, n_verts, n_faces);
+}
+
+int disn_mc_fetch(disn_ctx* c, float* verts, int32_t* faces) {
+  DISN_REQUIRE(c, "null ctx");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  return mc_fetch(c, verts, faces);
+}
+
+int disn_mc_write_obj(disn_ctx* c, const char* path) {
+  DISN_REQUIRE(c && path, "null argument");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  std::vector<float> v((size_t)c->mc_nv * 3);
+  std::vector<int32_t> f((size_t)c->mc_nf * 3);
+  if (mc_fetch(c, v.data(), f.data())) return -1;
+  return disn_write_obj(path, v.data(), c->mc_nv, f.data(), c->mc_nf);
+}
+
 int disn_marching_cubes(disn_ctx* c, const float* sdf, int32_t R, const double* bbox, float iso, float* verts,
                         int64_t* n_verts, int32_t* faces, int64_t* n_faces, uint32_t flags) {
   DISN_REQUIRE(c && sdf && bbox && n_verts && n_faces, "null argument");
-  DISN_REQUIRE(R >= 2, "need at least 2 samples per axis");
+  int64_t nv = 0, nf = 0;
+  const int rc = disn_mc_run(c, sdf, R, bbox, iso, flags, &nv, &nf);
+  if (rc) return rc;
+  if (verts == nullptr || faces == nullptr) { *n_verts = nv; *n_faces = nf; return 0; }     // counting call
+  if (*n_verts < nv || *n_faces < nf) { set_error("marching_cubes: output buffers too small"); return -2; }
+  *n_verts = nv; *n_faces = nf;
+  return mc_fetch(c, verts, faces);
+}
+
+int disn_eval_grid_resident(disn_ctx* c, const double* sdf_params, const float* trans_mat, int32_t B, int32_t sdf_res,
+                            float** out_dev) {
+  DISN_REQUIRE(c && sdf_params && trans_mat && out_dev, "null argument");
+  DISN_REQUIRE(sdf_res >= 1 && B >= 1, "sdf_res >= 1, B >= 1");
   DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
-  const float* d_sdf = sdf;
-  float* tmp = nullptr;
-  if (!(flags & DISN_DEVICE_PTR)) {
-    size_t nb = (size_t)R * R * R * sizeof(float);
-    DISN_CUDA_OK(cudaMalloc(&tmp, nb));
-    DISN_CUDA_OK(cudaMemcpyAsync(tmp, sdf, nb, cudaMemcpyHostToDevice, c->stream));
-    d_sdf = tmp;
+  const int R = sdf_res + 1;
+  const int64_t n = (int64_t)B * R * R * R;
+  if (n > c->grid_cap) {
+    if (c->d_grid) cudaFree(c->d_grid);
+    c->d_grid = nullptr; c->grid_cap = 0;
+    DISN_CUDA_OK(cudaMalloc(&c->d_grid, (size_t)n * sizeof(float)));
+    c->grid_cap = n;
   }
-  int rc = marching_cubes(c, d_sdf, R, bbox, iso, verts, n_verts, faces, n_faces, verts == nullptr || faces == nullptr);
-  cudaStreamSynchronize(c->stream);
-  if (tmp) cudaFree(tmp);
-  return rc;
+  DISN_CUDA_OK(cudaMemcpyAsync(c->d_tm, trans_mat, (size_t)B * 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  const int rc = disn_eval_grid(c, sdf_params, c->d_tm, B, sdf_res, 0, R, c->d_grid, DISN_DEVICE_PTR);
+  if (rc) return rc;
+  *out_dev = c->d_grid;
+  return 0;
+}
+
+int disn_fetch(disn_ctx* c, const void* dev, void* host, int64_t bytes) {
+  DISN_REQUIRE(c && dev && host && bytes >= 0, "bad fetch arguments");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  DISN_CUDA_OK(cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return check_status(c);
 }
 
 }  // extern "C"

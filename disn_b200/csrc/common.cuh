@@ -68,6 +68,8 @@ struct PointJob {
   // per-image encoder products
   const float* gbias;     // [B,512]
   const float* pmap;      // [B,img_h,img_w,512]
+  const float* pfeat;     // explicit-feature decoder (get_decoder): [B,N,512] per-point folded local features replace the
+                          // gather of pmap; nullptr on the fused path
   int32_t img_h, img_w;
   float clamp_max;
   float out_div;          // result divisor: 1 (eval_points) or sdf_weight (eval_grid)
@@ -78,6 +80,8 @@ struct PointJob {
   // outputs
   float* out_pred;        // [B,N]
   float* out_uv;          // [B,N,2] or nullptr
+  float* out_global;      // [B,N] pred_sdf_value_global (raw stream output) or nullptr
+  float* out_local;       // [B,N] pred_sdf_value_local or nullptr
   int* status;            // device word the kernels OR failure bits into (DISN_STATUS_*), or nullptr
 };
 
@@ -131,6 +135,17 @@ struct disn_ctx {
   bool tc_small_ok = false;
   float tc_small[2][2048] = {};         // host copy of the per-stream small parameters (the point kernel's __grid_constant__ table)
   std::map<std::string, uint8_t*> enc_tc_weights;   // packed bf16 hi/lo stage images of the encoder GEMMs
+  // marching cubes: persistent scratch + the device-resident mesh of the last run (mc.cu)
+  uint32_t* mc_edge_idx = nullptr; uint32_t* mc_cell_off = nullptr; uint32_t* mc_sums = nullptr;
+  uint32_t* mc_totals = nullptr; uint32_t* mc_totals_host = nullptr;
+  float* mc_verts = nullptr; int32_t* mc_faces = nullptr;
+  int64_t mc_pts_cap = 0, mc_verts_cap = 0, mc_faces_cap = 0, mc_nv = 0, mc_nf = 0;
+  // device-resident SDF grid of disn_eval_grid_resident and host staging for the marching-cubes input
+  float* d_grid = nullptr; int64_t grid_cap = 0;
+  float* d_mc_in = nullptr; int64_t mc_in_cap = 0;
+  // nn_distance / cam scratch (persistent, grows)
+  void* nn_scratch = nullptr; int64_t nn_scratch_bytes = 0;
+  void* dec_scratch = nullptr; int64_t dec_scratch_bytes = 0;   // explicit-feature decoder staging (decoder.cu)
 };
 
 namespace disn {
@@ -140,6 +155,13 @@ int encoder_run(disn_ctx* c, const float* imgs, int B, int H, int W, int C, bool
                 bool embedding_only = false);
 void encoder_free(disn_ctx* c);
 void encoder_graph_reset(disn_ctx* c);
+// api.cu
+int run_point_job(disn_ctx* c, PointJob& job);    // fills weights / encoder products / status and launches per cfg.precision
+int ensure_point_scratch(disn_ctx* c, int64_t pts);
+// encoder.cu helpers reused by the explicit-feature decoder
+int encoder_gemv(disn_ctx* c, const float* x, const float* W, const float* bias, float* out, int B, int K, int N, int relu);
+int encoder_gemm_plain(disn_ctx* c, const std::string& wname, const float* A, const float* Bm, const float* bias, float* C,
+                       int M, int N, int K, int relu);
 // point_fp32.cu
 int launch_point_fp32(disn_ctx* c, const PointJob& job);
 // point_tc.cu
@@ -155,6 +177,7 @@ int launch_cam_heads(disn_ctx* c, int B, const float* d_K, float* d_rt, float* d
 int nn_distance(disn_ctx* c, const float* d_xyz1, int n, const float* d_xyz2, int m, int B, float* d_dist1,
                 int* d_idx1, float* d_dist2, int* d_idx2);
 // mc.cu
-int marching_cubes(disn_ctx* c, const float* d_sdf, int R, const double* bbox, float iso,
-                   float* verts, int64_t* n_verts, int32_t* faces, int64_t* n_faces, bool count_only);
+int mc_run(disn_ctx* c, const float* d_sdf, int R, const double* bbox, float iso, int64_t* n_verts, int64_t* n_faces);
+int mc_fetch(disn_ctx* c, float* verts, int32_t* faces);
+void mc_free(disn_ctx* c);
 }  // namespace disn

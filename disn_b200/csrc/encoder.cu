@@ -452,6 +452,7 @@ int encoder_alloc(disn_ctx* c, int B) {
 }
 
 }  // namespace disn
+#ifdef DISN_DIAGNOSTICS
 // Diagnostic: run one GEMM (plain if H == 0, else 3x3 SAME im2col of an NHWC tensor) through both the fp32
 // CUDA-core kernel and the tcgen05 kernel; host pointers.  Used by the GPU test-suite to sweep shapes.
 extern "C" int disn_debug_gemm(disn_ctx* c, const float* A, const float* Wt, const float* bias, int M, int N, int K,
@@ -488,11 +489,22 @@ extern "C" int disn_debug_gemm(disn_ctx* c, const float* A, const float* Wt, con
   cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dC);
   return rc;
 }
+#endif  // DISN_DIAGNOSTICS
 namespace disn {
 
 static const float* wptr(disn_ctx* c, const std::string& name) {
   auto it = c->weights.find(name);
   return it == c->weights.end() ? nullptr : it->second.ptr;
+}
+
+int encoder_gemv(disn_ctx* c, const float* x, const float* W, const float* bias, float* out, int B, int K, int N, int relu) {
+  return launch_gemv(c, x, W, bias, out, B, K, N, relu);
+}
+int encoder_gemm_plain(disn_ctx* c, const std::string& wname, const float* A, const float* Bm, const float* bias, float* C,
+                       int M, int N, int K, int relu) {
+  if (encoder_alloc(c, 1)) return -1;     // split-K workspace
+  ConvGeom g{0, 0, 0};
+  return gemm_any(c, wname, A_PLAIN, A, Bm, bias, C, M, N, K, relu, g);
 }
 
 static int encoder_body(disn_ctx* c, int B, int H, int W, int C, bool embedding_only);

@@ -108,7 +108,7 @@ __device__ __forceinline__ void dense_layer(Smem& s, const float* __restrict__ i
 
 // one stream of the point MLP on the current tile; returns with s.act1[0..255][TP] = fold2/conv2 output
 template <bool LOCAL>
-__device__ __forceinline__ void run_stream(Smem& s, const PointJob& job, const StreamWeights& w, int b) {
+__device__ __forceinline__ void run_stream(Smem& s, const PointJob& job, const StreamWeights& w, int b, int64_t n0) {
   // fold1/conv1: 3 -> 64 (ReLU), into act0[64][TP]
   for (int i = threadIdx.x; i < 64 * TP; i += NTHREADS) {
     int f = i / TP, p = i % TP;
@@ -157,7 +157,14 @@ __device__ __forceinline__ void run_stream(Smem& s, const PointJob& job, const S
       for (int i = 0; i < 8; ++i) {
         float x = s.u[p0 + i], y = s.v[p0 + i];
         float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-        if (x > -1.f && y > -1.f && x < (float)Wm && y < (float)Hm) {
+        if (job.pfeat) {     // explicit per-point features (get_decoder): already folded through W[512:1984]
+          const int64_t n = n0 + p0 + i;
+          if (n < job.N) {
+            const float* q = job.pfeat + ((int64_t)b * job.N + n) * kHidden;
+            lo = __ldg(reinterpret_cast<const float4*>(q + f0));
+            hi = __ldg(reinterpret_cast<const float4*>(q + 256 + f0));
+          }
+        } else if (x > -1.f && y > -1.f && x < (float)Wm && y < (float)Hm) {
           int fx = (int)floorf(x), fy = (int)floorf(y);
           int cx = fx + 1, cy = fy + 1;
           float dx = (float)cx - x, dy = (float)cy - y;
@@ -242,7 +249,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_fp32_kernel(PointJob job, i
     __syncthreads();
 
     // ---- global stream ---------------------------------------------------------------------------
-    run_stream<false>(s, job, job.g, b);
+    run_stream<false>(s, job, job.g, b, n0);
     {  // fold2/conv5: 256 -> 1 (linear); warp w handles points w*4..w*4+3
       for (int pp = 0; pp < 4; ++pp) {
         int p = warp * 4 + pp;
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_fp32_kernel(PointJob job, i
     }
     __syncthreads();
     // ---- local stream -----------------------------------------------------------------------------
-    run_stream<true>(s, job, job.l, b);
+    run_stream<true>(s, job, job.l, b, n0);
     {
       for (int pp = 0; pp < 4; ++pp) {
         int p = warp * 4 + pp;
@@ -266,7 +273,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_fp32_kernel(PointJob job, i
         if (lane == 0) {
           const int64_t n = n0 + p;
           if (n < job.N) {
-            float r = s.pred[p] + (sum + job.l.b6[0]);     // pred_sdf = global + local (:204)
+            const float rl = sum + job.l.b6[0];
+            if (job.out_global) job.out_global[(int64_t)b * job.N + n] = s.pred[p];
+            if (job.out_local) job.out_local[(int64_t)b * job.N + n] = rl;
+            float r = s.pred[p] + rl;     // pred_sdf = global + local (:204)
             if (job.tanh_out) r = tanhf(r);
             job.out_pred[(int64_t)b * job.N + n] = __fdiv_rn(r, job.out_div);
           }

@@ -391,6 +391,8 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
           const float (*pp)[2][2][PTS] = s.part[it & 1];
           float rg = ((pp[0][0][0][p] + pp[0][0][1][p]) + (pp[0][1][0][p] + pp[0][1][1][p])) + __ldg(job.g.b6);
           float rl = ((pp[1][0][0][p] + pp[1][0][1][p]) + (pp[1][1][0][p] + pp[1][1][1][p])) + __ldg(job.l.b6);
+          if (job.out_global) job.out_global[(int64_t)tc0.b * job.N + n] = rg;
+          if (job.out_local) job.out_local[(int64_t)tc0.b * job.N + n] = rl;
           float r = rg + rl;
           if (job.tanh_out) r = tanhf(r);
           job.out_pred[(int64_t)tc0.b * job.N + n] = __fdiv_rn(r, job.out_div);
@@ -447,7 +449,9 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
         }
         int off[4] = {-1, -1, -1, -1};
         float wg[4] = {0.f, 0.f, 0.f, 0.f};
-        if (u > -1.f && v > -1.f && u < (float)Wm && v < (float)Hm) {
+        if (job.pfeat) {        // explicit per-point features: one "tap" of weight 1 at this point's row of pfeat
+          if (n < job.N) { off[0] = (int)(((int64_t)b * job.N + n) * kHidden); wg[0] = 1.f; }
+        } else if (u > -1.f && v > -1.f && u < (float)Wm && v < (float)Hm) {
           const int fx = (int)floorf(u), fy = (int)floorf(v);
           const int cx = fx + 1, cy = fy + 1;
           const float dx = (float)cx - u, dy = (float)cy - v;
@@ -475,7 +479,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
       const int b = tc0.b;
       const int pb = it & 1;
       if (it + 1 < my_tiles) compute_points(it + 1);
-      const float* pm = job.pmap + (int64_t)b * Hm * Wm * kHidden;
+      const float* pm = job.pfeat ? job.pfeat : job.pmap + (int64_t)b * Hm * Wm * kHidden;
       const int grp = lane >> 3, q = lane & 7;
       const bool pf = (job.pts == nullptr);
       auto prefetch_slice = [&](int t) {

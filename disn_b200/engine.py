@@ -117,6 +117,39 @@ class Engine:
             None if uv is None else uv.ctypes.data_as(C.c_void_p), 0))
         return (out, uv) if want_uv else out
 
+    def eval_points_ex(self, pts, trans_mat, pts_rot=None):
+        """pred_sdf, sample_img_points, pred_sdf_value_global, pred_sdf_value_local (model_normalization.py:194-206)."""
+        p, t = _f32(pts), _f32(trans_mat)
+        B, N, _ = p.shape
+        pr = None if pts_rot is None else _f32(pts_rot)
+        out, g, l = (np.empty((B, N, 1), np.float32) for _ in range(3))
+        uv = np.empty((B, N, 2), np.float32)
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        check(self.lib.disn_eval_points_ex(self._h, ptr(p), ptr(pr), ptr(t), B, N, ptr(out), ptr(uv), ptr(g), ptr(l)))
+        return out, uv, g, l
+
+    def point_img_feat(self, pts, trans_mat):
+        """end_points['point_img_feat'] [B,N,1,1472] and sample_img_points [B,N,2] (model_normalization.py:170-190)."""
+        p, t = _f32(pts), _f32(trans_mat)
+        B, N, _ = p.shape
+        feat = np.empty((B, N, 1, 1472), np.float32)
+        uv = np.empty((B, N, 2), np.float32)
+        check(self.lib.disn_point_img_feat(self._h, p.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), B, N,
+                                           feat.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p)))
+        return feat, uv
+
+    def eval_features(self, pts_rot, global_feat, point_feat):
+        """get_decoder (model_normalization.py:223-238): explicit [B,1,1,1024] / [B,N,1,1472] features ->
+        (multi_pred_sdf, pred_sdf_value_global, pred_sdf_value_local), each [B,N,1]."""
+        p = _f32(pts_rot)
+        B, N, _ = p.shape
+        g = _f32(global_feat).reshape(B, -1)
+        f = _f32(point_feat).reshape(B, N, 1472)
+        out, og, ol = (np.empty((B, N, 1), np.float32) for _ in range(3))
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(self.lib.disn_eval_features(self._h, ptr(p), ptr(g), ptr(f), B, N, ptr(out), ptr(og), ptr(ol), 0))
+        return out, og, ol
+
     def eval_points_device(self, pts_ptr: int, trans_mat_ptr: int, B: int, N: int, out_ptr: int,
                            uv_ptr: int = 0, pts_rot_ptr: int = 0):
         """Device-pointer, asynchronous variant (pointers from torch tensors' data_ptr())."""
@@ -194,8 +227,10 @@ class Engine:
         return p, r, 2 * p * r / np.maximum(p + r, 1e-30)
 
     # -- marching cubes -----------------------------------------------------------------------
-    def marching_cubes(self, sdf, bbox, iso: float = 0.0, device_ptr: int | None = None, R: int | None = None):
-        """sdf [R,R,R] (z,y,x) -> (verts [V,3] float32, faces [F,3] int32 0-based)."""
+    def marching_cubes(self, sdf, bbox, iso: float = 0.0, device_ptr: int | None = None, R: int | None = None,
+                       fetch: bool = True):
+        """sdf [R,R,R] (z,y,x) host array, or a device pointer -> (verts [V,3] float32, faces [F,3] int32 0-based).
+        The welded mesh also stays in HBM (write_mesh_obj); fetch=False returns only the counts."""
         bb = (C.c_double * 6)(*[float(v) for v in bbox])
         if device_ptr is None:
             a = _f32(sdf)
@@ -205,13 +240,45 @@ class Engine:
         else:
             ptr, flags = C.c_void_p(device_ptr), DISN_DEVICE_PTR
         nv, nf = C.c_int64(0), C.c_int64(0)
-        check(self.lib.disn_marching_cubes(self._h, ptr, R, bb, float(iso), None, C.byref(nv), None, C.byref(nf), flags))
+        check(self.lib.disn_mc_run(self._h, ptr, R, bb, float(iso), flags, C.byref(nv), C.byref(nf)))
+        if not fetch:
+            return nv.value, nf.value
         verts = np.empty((nv.value, 3), dtype=np.float32)
         faces = np.empty((nf.value, 3), dtype=np.int32)
         if nv.value and nf.value:
-            check(self.lib.disn_marching_cubes(self._h, ptr, R, bb, float(iso), verts.ctypes.data_as(C.c_void_p),
-                                               C.byref(nv), faces.ctypes.data_as(C.c_void_p), C.byref(nf), flags))
+            check(self.lib.disn_mc_fetch(self._h, verts.ctypes.data_as(C.c_void_p), faces.ctypes.data_as(C.c_void_p)))
         return verts, faces
+
+    def write_mesh_obj(self, path: str):
+        """OBJ of the mesh left in HBM by the last marching_cubes call (reference mesher's output conventions)."""
+        check(self.lib.disn_mc_write_obj(self._h, path.encode()))
+
+    def eval_grid_resident(self, sdf_params, trans_mat, sdf_res: int) -> int:
+        """Whole [B,R,R,R] grid evaluated into the context's HBM buffer; returns its device address."""
+        sp = np.ascontiguousarray(sdf_params, dtype=np.float64).reshape(-1, 6)
+        t = _f32(trans_mat)
+        out = C.c_void_p()
+        check(self.lib.disn_eval_grid_resident(self._h, sp.ctypes.data_as(C.POINTER(C.c_double)),
+                                               t.ctypes.data_as(C.c_void_p), sp.shape[0], sdf_res, C.byref(out)))
+        return int(out.value)
+
+    def fetch(self, dev_ptr: int, shape, dtype=np.float32) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        check(self.lib.disn_fetch(self._h, C.c_void_p(dev_ptr), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def iou(self, verts1, faces1, verts2, faces2, dim: int = 110, want_grids: bool = False):
+        """test/test_iou.py:208-233 iou_pymesh on two triangle meshes -> IoU (and the two occupancy grids)."""
+        v1, v2 = _f32(verts1), _f32(verts2)
+        f1, f2 = np.ascontiguousarray(faces1, np.int32), np.ascontiguousarray(faces2, np.int32)
+        inter, uni = C.c_int64(0), C.c_int64(0)
+        o1 = np.empty((dim, dim, dim), np.uint8) if want_grids else None
+        o2 = np.empty((dim, dim, dim), np.uint8) if want_grids else None
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        check(self.lib.disn_iou(self._h, ptr(v1), len(v1), ptr(f1), len(f1), ptr(v2), len(v2), ptr(f2), len(f2), dim,
+                                C.byref(inter), C.byref(uni), ptr(o1), ptr(o2)))
+        val = inter.value / uni.value if uni.value else float("nan")
+        return (val, inter.value, uni.value, o1, o2) if want_grids else val
 
 
 def write_dist(path: str, res: int, bbox, values):

@@ -111,11 +111,15 @@ def get_model(ref_dict, num_point, is_training, bn=False, bn_decay=None, img_siz
 
 
 def get_decoder(num_point, input_pls, feature_pls, bn=False, bn_decay=None, wd=None):
-    """models/model_normalization.py:223-238 -- decoder fed with explicit [B,N,1,1472] point features.
-    The fused kernel never materialises per-point features (that is the point of the design), so this
-    encoder/decoder split point is not offered."""
-    raise NotImplementedError("get_decoder feeds explicit per-point image features; the B200 path fuses the "
-                              "gather into the point kernel and has no such entry point")
+    """models/model_normalization.py:223-238 -- decoder fed with explicit features: feature_pls from
+    placeholder_features() ([B,1,1,1024] global embedding, [B,N,1,1472] per-point image features), input_pls from
+    placeholder_inputs() (only 'sample_pc_rot' is read).  Returns the symbolic multi_pred_sdf [B,N,1] (global + local).
+    Session.run folds the features through fold2/conv1's feature rows and runs the ordinary point kernel (disn_eval_features)."""
+    if bn:
+        raise NotImplementedError("bn=True is never used by the inference drivers")
+    g = _Graph(dict(input_pls, **feature_pls), None, num_point, None)
+    B, N = input_pls["sample_pc_rot"].shape[:2]
+    return Tensor("decoder_pred", g, (B, N, 1))
 
 
 def get_img_points(sample_pc, trans_mat_right):
@@ -179,7 +183,8 @@ class Session:
         rot = self._feed(feed_dict, pl.get("sample_pc_rot"))
         tm = self._feed(feed_dict, pl.get("trans_mat"))
         kinds = [f.kind for f in flist]
-        need_enc = any(k in ("pred_sdf", "img_embedding", "resized_ref_img") or k.startswith("loss:") for k in kinds)
+        need_enc = any(k in ("pred_sdf", "img_embedding", "resized_ref_img", "point_img_feat", "pred_sdf_value_global",
+                             "pred_sdf_value_local") or k.startswith("loss:") for k in kinds) and "decoder_pred" not in kinds
         if need_enc:
             if imgs is None:
                 raise ValueError("imgs placeholder was not fed")
@@ -188,8 +193,25 @@ class Session:
             if key != self._img_key:        # the reference re-runs VGG per chunk; once per image is enough
                 self.engine.encode(imgs)
                 self._img_key = key
-        pred = uv = None
-        if any(k in ("pred_sdf", "sample_img_points") or k.startswith("loss:") for k in kinds):
+        if "decoder_pred" in kinds:                     # get_decoder graph: explicit features, no encoder
+            if len(set(kinds)) != 1:
+                raise ValueError("fetch the decoder output on its own")
+            f_rot = self._feed(feed_dict, pl.get("sample_pc_rot"))
+            f_g = self._feed(feed_dict, pl.get("ref_feats_embedding_cnn"))
+            f_p = self._feed(feed_dict, pl.get("point_img_feat"))
+            if f_rot is None or f_g is None or f_p is None:
+                raise ValueError("sample_pc_rot / ref_feats_embedding_cnn / point_img_feat placeholders were not fed")
+            res = self.engine.eval_features(f_rot, f_g, f_p)[0]
+            return res if single else [res for _ in flist]
+        pred = uv = pg = plc = feat = None
+        want_streams = any(k in ("pred_sdf_value_global", "pred_sdf_value_local") for k in kinds)
+        if "point_img_feat" in kinds:
+            if pts is None or tm is None or self._img_key is None and imgs is None:
+                raise ValueError("sample_pc / trans_mat / imgs placeholders were not fed")
+            feat, _uv = self.engine.point_img_feat(pts, tm)
+        if want_streams:
+            pred, uv, pg, plc = self.engine.eval_points_ex(pts, tm, pts_rot=rot)
+        elif any(k in ("pred_sdf", "sample_img_points") or k.startswith("loss:") for k in kinds):
             if pts is None or tm is None:
                 raise ValueError("sample_pc / trans_mat placeholders were not fed")
             if self._img_key is None:        # projection only: any encoded image will do
@@ -202,7 +224,13 @@ class Session:
             if k == "pred_sdf":
                 out.append(pred)
             elif k == "sample_img_points":
-                out.append(uv)
+                out.append(uv if uv is not None else _uv)
+            elif k == "pred_sdf_value_global":
+                out.append(pg)
+            elif k == "pred_sdf_value_local":
+                out.append(plc)
+            elif k == "point_img_feat":
+                out.append(feat)
             elif k == "ref_img":
                 out.append(np.asarray(imgs))
             elif k == "img_embedding":

@@ -116,6 +116,20 @@ int disn_write_obj(const char* path, const float* verts, int64_t n_verts, const 
 int disn_marching_cubes(disn_ctx* ctx, const float* sdf, int32_t R, const double* bbox, float iso,
                         float* verts, int64_t* n_verts, int32_t* faces, int64_t* n_faces, uint32_t flags);
 
+/* Device-resident variant of the driver's tail (test/create_sdf.py:277-323 without the .dist round trip through the
+ * file system): disn_eval_grid_resident leaves the whole [B,R,R,R] grid (pred/sdf_weight) in HBM and returns its device
+ * address (valid until the next call on this context); disn_mc_run meshes one [R,R,R] field (device pointer with
+ * DISN_DEVICE_PTR, e.g. grid + b*R^3, or a host array) and keeps the welded mesh in HBM; disn_mc_fetch copies it to host
+ * buffers of n_verts*3 floats / n_faces*3 int32; disn_mc_write_obj writes it in disn_write_obj's format; disn_fetch is
+ * a synchronous device->host copy on the context's stream (e.g. to keep the .dist artefact). */
+int disn_eval_grid_resident(disn_ctx* ctx, const double* sdf_params, const float* trans_mat, int32_t B,
+                            int32_t sdf_res, float** out_dev);
+int disn_mc_run(disn_ctx* ctx, const float* sdf, int32_t R, const double* bbox, float iso, uint32_t flags,
+                int64_t* n_verts, int64_t* n_faces);
+int disn_mc_fetch(disn_ctx* ctx, float* verts, int32_t* faces);
+int disn_mc_write_obj(disn_ctx* ctx, const char* path);
+int disn_fetch(disn_ctx* ctx, const void* dev, void* host, int64_t bytes);
+
 /* Estimated-camera path (reference: demo/demo.py:195-258 cam_evl, cam_est/model_cam.py:47-109, models/posenet.py:91-124):
  * imgs host [B,H,W,3] -> VGG-16 embedding (the context's `vgg_16/...` weights = the camera checkpoint's) -> three FC
  * heads (`cameraprediction/{scale,ortho6d,translation}/fc{1,2,3}/{weights,biases}`) -> pred_RT [B,4,3] (or NULL) and
@@ -131,24 +145,29 @@ int disn_cam_estimate(disn_ctx* ctx, const float* imgs, int32_t B, int32_t H, in
 int disn_nn_distance(disn_ctx* ctx, const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M,
                      float* dist1, int32_t* idx1, float* dist2, int32_t* idx2);
 
-/* Diagnostic: one CTA-pair tcgen05 (cta_group::2) GEMM D[128x256] = A[128x64] * B[256x64]^T, `passes` times
- * accumulated; returns the raw TMEM image D_out[2 CTAs][128 lanes][128 columns]. Host pointers. */
-int disn_tc_selftest(int device, const float* A, const float* B, int passes, float* D_out);
-/* Diagnostic: mixed-kind accumulation used by DISN_PREC_F16F8 -- D = fp16(A16).fp16(B16)^T (mode bit 0) +
- * e5m2(A8).e5m2(B8)^T (mode bit 1) into one TMEM accumulator; A8q/B8q return the e5m2 values actually used. */
-int disn_tc_selftest_mixed(int device, const float* A16, const float* B16, const float* A8, const float* B8, int mode,
-                           float* A8q, float* B8q, float* D_out);
+/* IoU evaluator of the reference (test/test_iou.py:208-233 iou_pymesh): both triangle meshes (host float32 verts
+ * [nv,3], int32 0-based faces [nf,3]) are voxelised at cell 2/dim (restated pymesh.VoxelGrid: a cell centred at k*cell is
+ * occupied iff it overlaps a triangle), the corners of the occupied cells are binned with ((v+1.1)/2.4*dim) truncated, and
+ * the counts of the AND / OR of the two dim^3 occupancy grids are returned (IoU = intersection / union; dim = 110 in the
+ * reference).  occ1_out / occ2_out: optional uint8[dim^3] copies of the occupancy grids (index order [x][y][z]). */
+int disn_iou(disn_ctx* ctx, const float* verts1, int64_t nv1, const int32_t* faces1, int64_t nf1, const float* verts2,
+             int64_t nv2, const int32_t* faces2, int64_t nf2, int32_t dim, int64_t* intersection, int64_t* uni,
+             uint8_t* occ1_out, uint8_t* occ2_out);
 
-/* Diagnostic: one encoder GEMM (plain when H == 0, else the 3x3 SAME im2col view of NHWC A[M/(H*W),H,W,Cin]) through
- * the fp32 CUDA-core kernel and through the tcgen05 kernel; host pointers, outputs [M,N]. */
-int disn_debug_gemm(disn_ctx* ctx, const float* A, const float* Wt, const float* bias, int M, int N, int K, int H, int W,
-                    int Cin, int relu, float* out_fp32, float* out_tc);
-
-/* Diagnostic: prints the achievable L2 -> shared-memory bulk-copy streaming rate (bytes/clk/SM) for a sweep of
- * ring depths, stage sizes and cluster multicast widths (the weight-streaming pattern of the tensor-core kernel). */
-int disn_tc_stream_probe(int device);
-/* Diagnostic: prints the issue cost (cycles) of the mbarrier / tcgen05 synchronisation instructions of the MMA warp. */
-int disn_tc_op_probe(int device);
+/* Graph intermediates and the encoder/decoder split point of the reference (models/model_normalization.py:38-45,169-206,
+ * 223-238); host pointers, synchronous, not the hot path:
+ *   disn_eval_points_ex  = disn_eval_points + out_global / out_local [B,N,1] (end_points['pred_sdf_value_global'/'_local']);
+ *   disn_point_img_feat  = end_points['point_img_feat'] [B,N,1472] (5x resize-to-137 + resampler, concat conv1..conv5)
+ *                          and sample_img_points [B,N,2] (or NULL) for pts [B,N,3], trans_mat [B,4,3]; needs disn_encode;
+ *   disn_eval_features   = get_decoder: pts_rot [B,N,3], global_feat [B,num_classes], point_feat [B,N,1472] -> out_pred
+ *                          [B,N,1] = global + local (raw: no tanh, no /sdf_weight), out_global / out_local or NULL;
+ *                          needs the weights only. flags must be 0. */
+int disn_eval_points_ex(disn_ctx* ctx, const float* pts, const float* pts_rot, const float* trans_mat, int32_t B, int64_t N,
+                        float* out_pred, float* out_uv, float* out_global, float* out_local);
+int disn_point_img_feat(disn_ctx* ctx, const float* pts, const float* trans_mat, int32_t B, int64_t N, float* out_feat,
+                        float* out_uv);
+int disn_eval_features(disn_ctx* ctx, const float* pts_rot, const float* global_feat, const float* point_feat, int32_t B,
+                       int64_t N, float* out_pred, float* out_global, float* out_local, uint32_t flags);
 
 /* Kernel launch counter (bench's gpu_launches): number of this library's kernels launched so far. */
 int64_t disn_launch_count(disn_ctx* ctx);

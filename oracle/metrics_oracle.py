@@ -65,3 +65,71 @@ def precision_recall_f(pred, src, thresholds):
     p = (np.sqrt(df).reshape(1, -1) < th).mean(axis=1)
     r = (np.sqrt(db).reshape(1, -1) < th).mean(axis=1)
     return p, r, 2 * p * r / np.maximum(p + r, 1e-30)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# IoU (test/test_iou.py:208-233).  pymesh.VoxelGrid is an un-vendored third-party dependency (no pinned version, cannot be
+# loaded here): its voxeliser is restated -- cells k are cubes centred at k*cell with half-size cell/2 (PyMesh hash keys
+# are round(x / cell_size)), occupied iff they overlap a triangle (closed 13-axis separating-axis test), voxel-mesh
+# vertices = the 8 corners of every occupied cell.  The binning expression is the reference's.  PARITY UNPINNED vs PyMesh.
+# disn_b200/csrc/iou.cu performs the same float64 operations in the same order.
+# ----------------------------------------------------------------------------------------------------------------------
+def _tri_cube_overlap(c, half, tri):
+    """c [M,3] cube centres, tri [3,3] -> bool [M]; closed separating-axis test, same operation order as iou.cu."""
+    v = tri[None, :, :] - c[:, None, :]                      # [M,3(vertex),3(axis)]
+    ok = np.ones(len(c), bool)
+    for a in range(3):
+        mn = np.minimum(v[:, 0, a], np.minimum(v[:, 1, a], v[:, 2, a]))
+        mx = np.maximum(v[:, 0, a], np.maximum(v[:, 1, a], v[:, 2, a]))
+        ok &= ~((mn > half) | (mx < -half))
+    e = np.stack([v[:, 1] - v[:, 0], v[:, 2] - v[:, 1], v[:, 0] - v[:, 2]], axis=1)     # [M,3(edge),3]
+    nx = e[:, 0, 1] * e[:, 1, 2] - e[:, 0, 2] * e[:, 1, 1]
+    ny = e[:, 0, 2] * e[:, 1, 0] - e[:, 0, 0] * e[:, 1, 2]
+    nz = e[:, 0, 0] * e[:, 1, 1] - e[:, 0, 1] * e[:, 1, 0]
+    d = nx * v[:, 0, 0] + ny * v[:, 0, 1] + nz * v[:, 0, 2]
+    ok &= ~(np.abs(d) > half * (np.abs(nx) + np.abs(ny) + np.abs(nz)))
+
+    def sep(ax, ay, az):
+        p = [ax * v[:, k, 0] + ay * v[:, k, 1] + az * v[:, k, 2] for k in range(3)]
+        r = half * (np.abs(ax) + np.abs(ay) + np.abs(az))
+        return (np.minimum(p[0], np.minimum(p[1], p[2])) > r) | (np.maximum(p[0], np.maximum(p[1], p[2])) < -r)
+
+    z = np.zeros(len(c))
+    for i in range(3):
+        ok &= ~sep(z, -e[:, i, 2], e[:, i, 1])
+        ok &= ~sep(e[:, i, 2], z, -e[:, i, 0])
+        ok &= ~sep(-e[:, i, 1], e[:, i, 0], z)
+    return ok
+
+
+def voxel_occupancy(verts, faces, dim=110, vg=160, voff=80):
+    """occupancy grid [dim,dim,dim] uint8 of one mesh (the `v1` of test/test_iou.py:215-217)."""
+    cell = 2.0 / dim
+    V = np.asarray(verts, np.float32).astype(np.float64)
+    vox = set()
+    for f in np.asarray(faces):
+        tri = V[f]
+        lo, hi = tri.min(axis=0), tri.max(axis=0)
+        k0 = np.maximum(-voff, np.floor(lo / cell - 0.5).astype(int))
+        k1 = np.minimum(voff - 1, np.ceil(hi / cell + 0.5).astype(int))
+        if np.any(k1 < k0):
+            continue
+        ks = np.stack(np.meshgrid(*[np.arange(k0[a], k1[a] + 1) for a in range(3)], indexing="ij"), axis=-1).reshape(-1, 3)
+        hit = _tri_cube_overlap(ks.astype(np.float64) * cell, cell * 0.5, tri)
+        vox.update(map(tuple, ks[hit]))
+    occ = np.zeros((dim, dim, dim), np.uint8)
+    if vox:
+        ks = np.array(sorted(vox), np.float64)
+        for corner in np.ndindex(2, 2, 2):
+            p = (ks + (np.array(corner) - 0.5)) * cell
+            ind = ((p + 1.1) / 2.4 * dim).astype(int)
+            ok = np.all((ind >= 0) & (ind < dim), axis=1)
+            occ[ind[ok, 0], ind[ok, 1], ind[ok, 2]] = 1
+    return occ
+
+
+def iou_voxel(verts1, faces1, verts2, faces2, dim=110):
+    """test/test_iou.py:208-233 iou_pymesh: (intersection, union, iou)."""
+    a, b = voxel_occupancy(verts1, faces1, dim), voxel_occupancy(verts2, faces2, dim)
+    inter, union = int(np.logical_and(a, b).sum()), int(np.logical_or(a, b).sum())
+    return inter, union, (float(inter) / union if union else float("nan"))

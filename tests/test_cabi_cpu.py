@@ -11,8 +11,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_functions():
-    src = open(os.path.join(ROOT, "include", "disn_b200.h")).read()
+def _declared_functions(header="disn_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(disn_[a-z_0-9]+)\s*\(", src)))
 
@@ -25,6 +25,12 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
     assert set(names) == set(_lib.EXPORTS), "python binding and header disagree"
+    # diagnostics live in their own header / library; the product library must not export them
+    tlib = _lib.load_test()
+    tnames = _declared_functions("disn_b200_test.h")
+    assert set(tnames) == set(_lib.TEST_EXPORTS)
+    for n in tnames:
+        assert hasattr(tlib, n) and not hasattr(lib, n), n
 
 
 def test_write_dist_matches_golden(golden):

@@ -38,8 +38,6 @@ def test_session_run_matches_oracle_like_the_reference_driver(he_weights, precis
         assert np.abs(emb - ref["img_embedding"]).max() <= 2e-5 * np.abs(ref["img_embedding"]).max()
         m = orc.get_loss(ref["pred_sdf"], gt)
         assert abs(float(acc) - m["accuracy"]) < 0.01 and abs(float(real) - m["sdf_loss_realvalue"]) < 1e-4
-        with pytest.raises(NotImplementedError):
-            sess.run(ep["point_img_feat"], feed_dict=feed)
     finally:
         sess.close()
 

@@ -19,7 +19,7 @@ def test_tcgen05_cta_pair_gemm_layout(passes):
     """D = A.B^T through cta_group::2 lands in TMEM in the 2x2 datapath layout the point kernel assumes:
     CTA c, lane l, column j  <->  row c*64 + l%64, output column (l//64)*128 + j."""
     from disn_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_test()
     rng = np.random.default_rng(42)
     A = rng.standard_normal((128, 64)).astype(np.float32)
     B = rng.standard_normal((256, 64)).astype(np.float32)
@@ -158,7 +158,7 @@ def test_tc_encoder_matches_oracle(tc_engine, he_weights):
 def test_tc_selftest_mixed_kinds(mode):
     """kind::f16 (fp16, SW128) and kind::f8f6f4 (e5m2, SW64) MMAs accumulating into the same TMEM tile."""
     from disn_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_test()
     rng = np.random.default_rng(mode)
     A16 = rng.standard_normal((128, 64)).astype(np.float32)
     B16 = rng.standard_normal((256, 64)).astype(np.float32)

@@ -142,3 +142,27 @@ def test_nn_distance_oracle_matches_reference_golden(golden):
         got = mo.nn_distance(g[name + "_xyz1"], g[name + "_xyz2"])
         for arr, key in zip(got, ("_dist1", "_idx1", "_dist2", "_idx2")):
             np.testing.assert_array_equal(arr, g[name + key], err_msg=name + key)
+
+
+def test_iou_oracle_properties():
+    """oracle/metrics_oracle.iou_voxel (restated test/test_iou.py:208-233): identity, disjointness, monotone overlap."""
+    from oracle import metrics_oracle as mo
+
+    def box(lo, hi):
+        lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+        v = np.array([[x, y, z] for z in (lo[2], hi[2]) for y in (lo[1], hi[1]) for x in (lo[0], hi[0])], np.float32)
+        f = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6],
+                      [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], np.int32)
+        return v, f
+    a = box((-0.3, -0.3, -0.3), (0.3, 0.3, 0.3))
+    b = box((-0.3, -0.3, -0.3), (0.3, 0.3, 0.1))
+    c = box((0.6, 0.6, 0.6), (0.8, 0.8, 0.8))
+    assert mo.iou_voxel(*a, *a, dim=32)[2] == 1.0
+    assert mo.iou_voxel(*a, *c, dim=32)[2] == 0.0
+    i_ab = mo.iou_voxel(*a, *b, dim=32)[2]
+    assert 0.3 < i_ab < 1.0
+    occ = mo.voxel_occupancy(*a, dim=32)
+    assert occ.sum() > 0 and occ[0, 0, 0] == 0          # surface voxels only, binned inside the grid
+    # the surface of the box is hollow in the occupancy grid: the centre bin is empty
+    ctr = int((0.0 + 1.1) / 2.4 * 32)
+    assert occ[ctr, ctr, ctr] == 0

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from disn_b200 import _lib
 from disn_b200.engine import Engine
 eng = Engine(device=0, precision="fp32")
-lib = _lib.load()
+lib = _lib.load_test()
 rng = np.random.default_rng(0)
 def run(M, N, K, H=0, W=0, Cin=0, bias=True, relu=1):
     A = rng.standard_normal((M, Cin if H else K)).astype(np.float32)

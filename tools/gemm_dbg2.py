@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from disn_b200 import _lib
 from disn_b200.engine import Engine
 eng = Engine(device=0, precision="fp32")
-lib = _lib.load()
+lib = _lib.load_test()
 def run(M, N, K, mode):
     # structured inputs: A = ones, W[k, n] = indicator of K-slice -> output counts which slices contributed
     A = np.ones((M, K), np.float32)
