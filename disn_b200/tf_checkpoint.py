@@ -7,8 +7,11 @@
     engine.load_weights(weights)
 
 Format (restated from TensorFlow's tensor_bundle / leveldb-table sources, which are not vendored in the
-reference; UNPINNED against a real checkpoint -- the authors' files are Dropbox downloads -- and therefore
-covered by a writer/reader round trip only):
+reference).  The authors' files are Dropbox downloads, so there is no TF-written bundle to pin against; the reader is
+pinned instead by tests/tf_bundle_golden.py, which assembles a bundle byte by byte from the documented table layout
+(prefix-compressed keys, 16-entry restart intervals, several data blocks, shortened index keys, crc32c known-answer
+vectors from RFC 3720) WITHOUT using this module's writer, and by negative tests (snappy-flagged block, corrupted CRC,
+truncated data shard).  Layout:
   * .index is an SSTable: data blocks of prefix-compressed (key, value) entries + restart array, a 5-byte block
     trailer (compression type, masked crc32c), an index block mapping last-keys to block handles, and a 48-byte
     footer (metaindex handle, index handle, padding, magic 0xdb4775248b80fb57);
@@ -90,16 +93,23 @@ def _block_entries(block):
         pos += vlen
 
 
-def _read_block(data, offset, size):
+def _read_block(data, offset, size, verify=True):
+    if offset + size + 5 > len(data):
+        raise ValueError("table block handle (%d, %d) points outside the file" % (offset, size))
     ctype = data[offset + size]
     if ctype != 0:
-        raise NotImplementedError("compressed table blocks (type %d) are not supported; re-save the checkpoint "
-                                  "uncompressed" % ctype)
+        raise NotImplementedError("compressed table blocks (type %d; 1 = snappy) are not supported; re-save the "
+                                  "checkpoint uncompressed" % ctype)
+    if verify:
+        stored = struct.unpack_from("<I", data, offset + size + 1)[0]
+        if stored != _masked_crc32c(data[offset:offset + size + 1]):
+            raise ValueError("table block at offset %d fails its crc32c check (corrupt .index)" % offset)
     return data[offset:offset + size]
 
 
-def read_index(index_path):
-    """-> {tensor_name: dict(dtype, shape, shard_id, offset, size)}"""
+def read_index(index_path, with_header=False):
+    """-> {tensor_name: dict(dtype, shape, shard_id, offset, size, crc32c)}; with_header=True -> (entries, header) where
+    header = dict(num_shards, endianness, version) from the BundleHeaderProto stored under the empty key."""
     data = open(index_path, "rb").read()
     if len(data) < 48 or struct.unpack_from("<Q", data, len(data) - 8)[0] != TABLE_MAGIC:
         raise ValueError("%s is not a TensorFlow checkpoint index (bad table magic)" % index_path)
@@ -110,37 +120,71 @@ def read_index(index_path):
     ioff, pos = _varint(footer, pos)
     isize, pos = _varint(footer, pos)
     entries = {}
+    header = dict(num_shards=1, endianness=0, version=None)
     for _, handle in _block_entries(_read_block(data, ioff, isize)):
         boff, p = _varint(handle, 0)
         bsize, p = _varint(handle, p)
         for key, value in _block_entries(_read_block(data, boff, bsize)):
-            if key == b"":
-                continue                    # BundleHeaderProto
+            if key == b"":                  # BundleHeaderProto {1: num_shards, 2: endianness, 3: version{1: producer}}
+                h = _parse_proto(value)
+                header["num_shards"] = h.get(1, [1])[0]
+                header["endianness"] = h.get(2, [0])[0]
+                if 3 in h:
+                    header["version"] = _parse_proto(h[3][0]).get(1, [0])[0]
+                if header["endianness"] != 0:
+                    raise NotImplementedError("big-endian tensor bundles are not supported")
+                continue
             e = _parse_proto(value)
             shape = []
             if 2 in e:
                 for dim in _parse_proto(e[2][0]).get(2, []):
                     shape.append(_parse_proto(dim).get(1, [0])[0])
             entries[key.decode()] = dict(dtype=e.get(1, [0])[0], shape=tuple(shape), shard_id=e.get(3, [0])[0],
-                                         offset=e.get(4, [0])[0], size=e.get(5, [0])[0])
-    return entries
+                                         offset=e.get(4, [0])[0], size=e.get(5, [0])[0], crc32c=e.get(6, [None])[0],
+                                         sliced=7 in e)
+    return (entries, header) if with_header else entries
 
 
-def load_checkpoint(prefix, prefixes=None):
-    """Read every variable (optionally only names starting with one of `prefixes`) as numpy arrays."""
-    index = read_index(prefix + ".index")
+# optimizer slots / moving averages / step counters a tf.train.Saver checkpoint carries next to the model variables
+_SLOT_SUFFIXES = ("/Adam", "/Adam_1", "/Momentum", "/ExponentialMovingAverage", "/RMSProp", "/RMSProp_1")
+_BOOKKEEPING = ("global_step", "beta1_power", "beta2_power")
+
+
+def is_model_variable(name: str) -> bool:
+    return not name.endswith(_SLOT_SUFFIXES) and name.split("/")[-1] not in _BOOKKEEPING
+
+
+def load_checkpoint(prefix, prefixes=None, model_variables_only=True, verify_data=False):
+    """Read the variables (optionally only names starting with one of `prefixes`) as numpy arrays.
+    model_variables_only drops optimizer slots (`.../Adam`, `.../Adam_1`, ...) and step counters, which would otherwise
+    triple the upload; verify_data=True checks every tensor's crc32c (pure Python: slow for the 554 MB of VGG-16)."""
+    index, header = read_index(prefix + ".index", with_header=True)
     shards = {}
     out = {}
-    num_shards = max(e["shard_id"] for e in index.values()) + 1 if index else 1
+    num_shards = header["num_shards"]
     for name, e in index.items():
         if prefixes and not name.startswith(tuple(prefixes)):
             continue
+        if model_variables_only and not is_model_variable(name):
+            continue
         if e["dtype"] not in DTYPES:
             continue                        # non-numeric bookkeeping entries
+        if e["sliced"]:
+            raise NotImplementedError("%s is stored as slices (partitioned variable); not supported" % name)
         sid = e["shard_id"]
+        if sid >= num_shards:
+            raise ValueError("%s refers to shard %d of %d" % (name, sid, num_shards))
         if sid not in shards:
             shards[sid] = np.memmap("%s.data-%05d-of-%05d" % (prefix, sid, num_shards), dtype=np.uint8, mode="r")
+        if e["offset"] + e["size"] > shards[sid].size:
+            raise ValueError("%s: data shard %d is truncated (%d + %d > %d bytes)" % (name, sid, e["offset"], e["size"],
+                                                                                    shards[sid].size))
+        want = int(np.prod(e["shape"], dtype=np.int64)) * np.dtype(DTYPES[e["dtype"]]).itemsize
+        if want != e["size"]:
+            raise ValueError("%s: %d bytes stored for shape %s" % (name, e["size"], e["shape"]))
         raw = np.asarray(shards[sid][e["offset"]:e["offset"] + e["size"]])
+        if verify_data and e["crc32c"] is not None and _masked_crc32c(raw.tobytes()) != e["crc32c"]:
+            raise ValueError("%s fails its crc32c check (corrupt data shard)" % name)
         out[name] = raw.view(DTYPES[e["dtype"]]).reshape(e["shape"]).copy()
     return out
 
@@ -161,11 +205,17 @@ def _crc32c_table():
 _CRC_TBL = _crc32c_table()
 
 
-def _masked_crc32c(data):
+def crc32c(data) -> int:
+    """CRC-32C (Castagnoli, reflected polynomial 0x82F63B78), as in RFC 3720 appendix B.4."""
     c = 0xFFFFFFFF
-    for b in data:
+    for b in bytes(data):
         c = _CRC_TBL[(c ^ b) & 0xFF] ^ (c >> 8)
-    c ^= 0xFFFFFFFF
+    return c ^ 0xFFFFFFFF
+
+
+def _masked_crc32c(data):
+    """leveldb / TensorFlow store crcs "masked": rotate right by 15 bits and add a constant."""
+    c = crc32c(data)
     return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
 
 
@@ -173,10 +223,13 @@ def _field(num, wt, payload):
     return _put_varint((num << 3) | wt) + payload
 
 
-def _entry_proto(dtype, shape, offset, size):
+def _entry_proto(dtype, shape, offset, size, crc=None):
     dims = b"".join(_field(2, 2, _put_varint(len(d)) + d) for d in (_field(1, 0, _put_varint(s)) for s in shape))
-    return (_field(1, 0, _put_varint(dtype)) + _field(2, 2, _put_varint(len(dims)) + dims) +
-            _field(4, 0, _put_varint(offset)) + _field(5, 0, _put_varint(size)))
+    out = (_field(1, 0, _put_varint(dtype)) + _field(2, 2, _put_varint(len(dims)) + dims) +
+           _field(4, 0, _put_varint(offset)) + _field(5, 0, _put_varint(size)))
+    if crc is not None:
+        out += _field(6, 5, struct.pack("<I", crc))     # fixed32 crc32c (masked)
+    return out
 
 
 def _build_block_multi(items):
@@ -197,7 +250,7 @@ def save_checkpoint(prefix, tensors):
             a = np.ascontiguousarray(tensors[name])
             raw = a.tobytes()
             f.write(raw)
-            items.append((name.encode(), _entry_proto(DTYPE_CODES[a.dtype], a.shape, offset, len(raw))))
+            items.append((name.encode(), _entry_proto(DTYPE_CODES[a.dtype], a.shape, offset, len(raw), _masked_crc32c(raw))))
             offset += len(raw)
     out = bytearray()
     index_items = []

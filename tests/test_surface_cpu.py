@@ -159,3 +159,67 @@ def test_demo_image_loader_and_gt_camera(tmp_path):
         demo.read_img_get_transmat(str(tmp_path / "missing.png"))
     with pytest.raises(RuntimeError):           # --cam_est without the camera checkpoint's variables
         demo.read_img_get_transmat(path, cam_est=True)
+
+
+def test_tf_checkpoint_reader_against_independently_assembled_bundle(tmp_path):
+    """The reader is pinned by a bundle assembled byte by byte from the documented table layout by tests/tf_bundle_golden.py
+    (no code shared with the module's writer): prefix-compressed keys, 16-entry restarts, several blocks, shortened index
+    keys, two data shards, optimizer slots + global_step; plus crc32c known answers and the loud failure modes."""
+    import struct
+    from disn_b200 import synth, tf_checkpoint as ck
+    from tests import tf_bundle_golden as gb
+    # crc32c known-answer vectors (RFC 3720 B.4) for both implementations
+    kat = [(b"123456789", 0xE3069283), (bytes(32), 0x8A9136AA), (b"\xff" * 32, 0x62A8AB43), (bytes(range(32)), 0x46DD794E),
+           (bytes(range(31, -1, -1)), 0x113FDB5C)]
+    for data, want in kat:
+        assert gb.crc32c_bitwise(data) == want and ck.crc32c(data) == want
+    assert ck._masked_crc32c(b"123456789") == gb.mask(0xE3069283)
+    rng = np.random.default_rng(0)
+    shapes = {k: v for k, v in synth.weight_shapes().items() if "fc6" not in k and "fc7" not in k}   # keep it small
+    tensors = {}
+    for name, shp in shapes.items():
+        small = tuple(min(d, 6) for d in shp)                 # many entries, few bytes
+        tensors[name] = rng.standard_normal(small).astype(np.float32)
+        if name.endswith("weights"):
+            tensors[name + "/Adam"] = np.zeros(small, np.float32)
+            tensors[name + "/Adam_1"] = np.zeros(small, np.float32)
+    tensors["global_step"] = np.array(123456, np.int64)
+    tensors["beta1_power"] = np.array(0.5, np.float32)
+    prefix = str(tmp_path / "model.ckpt")
+    shard_of = lambda n: 1 if n.startswith("sdfprediction_imgfeat") else 0
+    idx = gb.write_bundle(prefix, tensors, num_shards=2, shard_of=shard_of, block_size=512)
+    entries, header = ck.read_index(prefix + ".index", with_header=True)
+    assert header == dict(num_shards=2, endianness=0, version=1)
+    assert set(entries) == set(tensors) and len(idx) > 6 * 512             # several data blocks, multi-entry index block
+    assert entries["sdfprediction_imgfeat/fold2/conv1/weights"]["shard_id"] == 1
+    got = ck.load_checkpoint(prefix, prefixes=("vgg_16/", "sdfprediction"), verify_data=True)
+    want = {k: v for k, v in tensors.items() if ck.is_model_variable(k) and k.startswith(("vgg_16/", "sdfprediction"))}
+    assert set(got) == set(want) and not any(k.endswith(("/Adam", "/Adam_1")) for k in got)
+    for k in want:
+        np.testing.assert_array_equal(got[k], want[k])
+    everything = ck.load_checkpoint(prefix, model_variables_only=False)
+    assert everything["global_step"] == 123456 and "vgg_16/conv1/conv1_1/weights/Adam_1" in everything
+    # the module's own writer must produce something this reader AND the independent expectations agree on
+    ck.save_checkpoint(str(tmp_path / "own.ckpt"), {k: tensors[k] for k in list(want)[:20]})
+    own = ck.read_index(str(tmp_path / "own.ckpt.index"))
+    for k, e in own.items():
+        assert e["crc32c"] == gb.mask(gb.crc32c_bitwise(tensors[k].tobytes()))
+    # failure modes are loud: snappy-flagged blocks, a flipped byte in a data block, a truncated shard, a corrupted tensor
+    gb.write_bundle(str(tmp_path / "snappy.ckpt"), want, compression_type=1)
+    with pytest.raises(NotImplementedError, match="snappy"):
+        ck.read_index(str(tmp_path / "snappy.ckpt.index"))
+    bad = bytearray(idx)
+    bad[100] ^= 0x40
+    open(str(tmp_path / "bad.ckpt.index"), "wb").write(bytes(bad))
+    with pytest.raises(ValueError, match="crc32c"):
+        ck.read_index(str(tmp_path / "bad.ckpt.index"))
+    d0 = prefix + ".data-00000-of-00002"
+    raw = open(d0, "rb").read()
+    open(d0, "wb").write(raw[:-16])
+    with pytest.raises(ValueError, match="truncated"):
+        ck.load_checkpoint(prefix, model_variables_only=False)
+    flipped = bytearray(raw)
+    flipped[5] ^= 1
+    open(d0, "wb").write(bytes(flipped))
+    with pytest.raises(ValueError, match="crc32c"):
+        ck.load_checkpoint(prefix, verify_data=True, model_variables_only=False)
