@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -97,7 +98,8 @@ struct disn_ctx {
   bool weights_dirty = true;
   int64_t launches = 0;
   int num_sms = 148;            // cudaDevAttrMultiProcessorCount of cfg.device, read once in disn_create
-  bool attr_conv_tc = false, attr_point_fp32 = false, attr_point_tc[4] = {false, false, false, false};   // cudaFuncSetAttribute done on this device
+  bool attr_conv_tc = false, attr_point_fp32 = false;   // cudaFuncSetAttribute done on this device
+  std::set<const void*> attr_done;                      // ... for the point_tc_kernel instantiations
 
   // encoder state
   int32_t enc_B = 0;
@@ -136,7 +138,7 @@ struct disn_ctx {
   float tc_small[2][2048] = {};         // host copy of the per-stream small parameters (the point kernel's __grid_constant__ table)
   std::map<std::string, uint8_t*> enc_tc_weights;   // packed bf16 hi/lo stage images of the encoder GEMMs
   // marching cubes: persistent scratch + the device-resident mesh of the last run (mc.cu)
-  uint32_t* mc_edge_idx = nullptr; uint32_t* mc_cell_off = nullptr; uint32_t* mc_sums = nullptr;
+  uint8_t* mc_code = nullptr; uint32_t* mc_vbase = nullptr; uint32_t* mc_chunk = nullptr; uint32_t* mc_sums = nullptr;
   uint32_t* mc_totals = nullptr; uint32_t* mc_totals_host = nullptr;
   float* mc_verts = nullptr; int32_t* mc_faces = nullptr;
   int64_t mc_pts_cap = 0, mc_verts_cap = 0, mc_faces_cap = 0, mc_nv = 0, mc_nf = 0;

@@ -5,8 +5,9 @@
 // wide layers of each stream run on the 5th-gen tensor cores.  To hold the reference's 1e-4 bar the fp32 operands
 // are split (template parameter kMode):
 //   MODE_BF16X3  x = hi + lo (two bf16), each product = 3 kind::f16 MMAs (hi*hi + lo*hi + hi*lo), error ~2^-17;
-//   MODE_F16F8   fp16 main product + two e5m2 first-order correction products (kind::f8f6f4, twice the rate) into the
-//                same fp32 accumulator in TMEM: 2 MMA-units per product instead of 3.
+//   MODE_F16F8   fp16 main product + e5m2 first-order correction products (kind::f8f6f4, twice the rate) into the
+//                same fp32 accumulator in TMEM: both corrections (2 MMA-units per product instead of 3) in every layer
+//                but fold2/conv1, which keeps one (1.5 units): 1.76 units per product overall.
 //
 // Organisation (one CTA pair = one cluster of 2, cta_group::2, UMMA M=128 x N=256 x K=16|32):
 //   * a pair-tile is 128 query points, 64 per CTA (the 2x2 datapath keeps a 512-wide fp32 layer output
@@ -52,6 +53,8 @@ namespace disn {
 namespace {
 
 constexpr int NW = 4;                 // weight ring stages
+constexpr int CORR_DEFAULT = 0xDF;    // correction mask of DISN_PREC_F16F8 (see kCorr below): every correction except the
+                                      // a.(w - h(w)) product of fold2/conv1 -- measured on B200 (profiles/r02_corr_mask_sweep.txt)
 #include "point_tc_shared.cuh"
 
 constexpr int RING_PER_STREAM = 21;   // X3 (4) + X4 (8) + next stream's X2 (1) + X5 (8)
@@ -103,9 +106,18 @@ __device__ __forceinline__ uint32_t ring_seq(int sn, int kind, int t, int nstrea
 
 // kVar bit 0: measurement build -- `expt` masks MMA groups (1 main product, 2 first correction, 4 second correction) and
 //             every CTA reports its cycle count (DISN_TC_MEASURE=1 [DISN_TC_EXPT=<mask>]; masked results are wrong by
-//             construction).  The product build (kVar = 0) carries none of it.
+//             construction).  The product build carries none of it.
+// kCorr (MODE_F16F8): which correction products each tensor layer keeps -- bit 2l: (a - h(a)).w ("first"), bit 2l+1:
+//             a.(w - h(w)) ("second") for tensor layer l = 0..3 (fold1/conv2, fold1/conv3, fold2/conv1, fold2/conv2).  A dropped
+//             correction saves its MMAs, its 8 KB weight tile per stage (not copied) and its e5m2 A tile (not produced by
+//             the epilogue).  0xFF = every correction (2 bf16-rate units per product); the shipped mask is CORR_DEFAULT.
 #define WAIT(bar, par) tc::mbar_wait(bar, par)
-template <int kMode, int kVar>
+// tensor layer of a weight stage from its position in the per-tile consumption cycle
+//   G.L1 0..7 | G.L2 8..23 | L.L0 24 | G.L3 25..32 | L.L1 33..40 | L.L2 41..56 | G.L0 57 | L.L3 58..65
+__host__ __device__ constexpr int stage_layer(uint32_t r) {
+  return r < 8 ? 1 : r < 24 ? 2 : r == 24 ? 0 : r < 33 ? 3 : r < 41 ? 1 : r < 57 ? 2 : r == 57 ? 0 : 3;
+}
+template <int kMode, int kVar, int kCorr>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint8_t* __restrict__ wpk,
                  int64_t tiles_per_img, unsigned long long* __restrict__ dbg, int expt) {
@@ -114,6 +126,9 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
   const uint32_t cta = tc::cluster_ctarank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tid = threadIdx.x;
+  constexpr int kC = (kMode == MODE_F16F8) ? kCorr : 0xFF;      // bf16x3 has no droppable products
+  auto keep1 = [](int layer) { return ((kC >> (2 * layer)) & 1) != 0; };
+  auto keep2 = [](int layer) { return ((kC >> (2 * layer + 1)) & 1) != 0; };
   const int num_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int64_t total_tiles = tiles_per_img * job.B;
   const int my_tiles = (pair < total_tiles) ? (int)((total_tiles - pair + num_pairs - 1) / num_pairs) : 0;
@@ -158,9 +173,14 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
         stage_info(g, my_tiles, img_stage, issuer);
         uint64_t* bar = &s.wfull[cta == 0 ? issuer : 0][slot];
         const uint8_t* src = wpk + (size_t)img_stage * (2 * W_STAGE) + (size_t)cta * W_STAGE + (size_t)lane * W_TILE;
-        tc::bulk_g2s(s.w[slot] + lane * W_TILE, src, W_TILE, bar);
+        // lane 0: the main tile; lane 1: the e5m2 tiles of the corrections this layer keeps ([e5m2 w | e5m2 residual of w])
+        const int sl = stage_layer(img_stage);
+        const bool k1 = keep1(sl), k2 = keep2(sl);
+        if (lane == 0) tc::bulk_g2s(s.w[slot], src, W_TILE, bar);
+        else if (k1 || k2)
+          tc::bulk_g2s(s.w[slot] + W_TILE + (k1 ? 0 : W8_TILE), src + (k1 ? 0 : W8_TILE), (k1 && k2) ? W_TILE : W8_TILE, bar);
         // the byte count may be posted after the copies: the phase cannot complete before this arrival
-        if (lane == 0) tc::mbar_arrive_expect_tx(bar, W_STAGE);
+        if (lane == 0) tc::mbar_arrive_expect_tx(bar, W_TILE + (k1 ? W8_TILE : 0) + (k2 ? W8_TILE : 0));
         __syncwarp(0x3);
       }
     }
@@ -234,11 +254,11 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tc::mma_cg2_lo(d, a_hi + 2u * k, b_hi + 2u * k, idesc, (t | k) ? 1u : 0u);
                   }
-                  if (x1) {
+                  if (x1 && keep1(layer)) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) tc::mma_cg2_f8_lo(d, a_lo + 2u * k, b_lo + 2u * k, idesc8, 1u);
                   }
-                  if (x2) {
+                  if (x2 && keep2(layer)) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k)
                       tc::mma_cg2_f8_lo(d, a_lo + (X8_TILE >> 4) + 2u * k, b_lo + (W8_TILE >> 4) + 2u * k, idesc8, 1u);
@@ -294,13 +314,13 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
         v[j] = fmaxf(a, 0.f);
       }
       WAIT(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
-      store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, job.act_scale[sx][0][0], job.act_scale[sx][0][1], amax);
+      store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, job.act_scale[sx][0][0], job.act_scale[sx][0][1], amax, keep1(0), keep2(0));
       arrive_xfull(slot);
     };
     // drain thread-columns [32t, 32t+32) of the accumulator at `col0` into ring slice `seq`; the bias comes from the
     // parameter table (sb_off, stream sx) or, for the global stream's fold2/conv1, from the per-image folded bias in HBM
     auto drain = [&](uint32_t col0, int t, int sx, int sb_off, const float* gbias, uint32_t seq, bool gather, float sc_lo,
-                     float sc_hi, uint64_t* accbar, uint32_t accpar) {
+                     float sc_hi, uint64_t* accbar, uint32_t accpar, int next_layer) {
       const int slot = (int)(seq % NX);
       if (accbar) {
         WAIT(accbar, accpar);
@@ -332,7 +352,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + v[j], 0.f);
       WAIT(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
-      store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, sc_lo, sc_hi, amax);
+      store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, sc_lo, sc_hi, amax, keep1(next_layer), keep2(next_layer));
       arrive_xfull(slot);
       if (gather && lane == 0) tc::mbar_arrive(&s.gempty[gs]);
     };
@@ -340,7 +360,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
       const int sx = sn & 1;
       for (int t = eg; t < 4; t += 2)
         drain(acc_col(0, sx), t, sx, SB_B2, nullptr, ring_seq(sn, 3, t, nstreams), false, job.act_scale[sx][1][0],
-              job.act_scale[sx][1][1], t == eg ? &s.acc_full[0][0] : nullptr, (uint32_t)sn & 1);
+              job.act_scale[sx][1][1], t == eg ? &s.acc_full[0][0] : nullptr, (uint32_t)sn & 1, 1);
     };
 
     // ring order: X2_0, then per stream n: X3_n (4), X4_n (8), X2_{n+1}, X5_n (8); X3_{n+1} before stream n's final layer
@@ -354,12 +374,12 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
       const uint32_t par = (uint32_t)sn & 1;
       for (int t = eg; t < 8; t += 2)
         drain(acc_col(1, sidx), t, sidx, SB_B3, nullptr, ring_seq(sn, 4, t, nstreams), false, job.act_scale[sidx][2][0],
-              job.act_scale[sidx][2][1], t == eg ? &s.acc_full[1][0] : (t == eg + 4 ? &s.acc_full[1][1] : nullptr), par);
+              job.act_scale[sidx][2][1], t == eg ? &s.acc_full[1][0] : (t == eg + 4 ? &s.acc_full[1][1] : nullptr), par, 2);
       if (eg == 0 && sn + 1 < nstreams) stage_first(sn + 1);
       const float* gb = sidx ? nullptr : (job.gbias + (int64_t)tc0.b * kHidden);
       for (int t = eg; t < 8; t += 2)
         drain(acc_col(2, sidx), t, sidx, SB_B4, gb, ring_seq(sn, 5, t, nstreams), sidx == 1, job.act_scale[sidx][3][0],
-              job.act_scale[sidx][3][1], t == eg ? &s.acc_full[2][0] : (t == eg + 4 ? &s.acc_full[2][1] : nullptr), par);
+              job.act_scale[sidx][3][1], t == eg ? &s.acc_full[2][0] : (t == eg + 4 ? &s.acc_full[2][1] : nullptr), par, 3);
       if (sn + 1 < nstreams) drain_x3(sn + 1);
       // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
       WAIT(&s.acc_full[3][0], par);
@@ -550,15 +570,15 @@ inline int fin_of(int layer, int t, int k) {
   return fout(k / 32, c);
 }
 
-template <int kMode, int kVar>
+template <int kMode, int kVar, int kCorr>
 int launch_var(disn_ctx* c, const PointJob& job, const SmallParams& sp, const void* wpk, int pairs, int smem,
                int64_t tiles_per_img) {
-  // the attribute belongs to (function, device): remembered per context, not per process (a second engine on another
-  // device in the same process would otherwise launch with the 48 KB default)
-  bool& attr = c->attr_point_tc[kMode * 2 + (kVar & 1)];
-  if (!attr) {
-    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<kMode, kVar>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
+  // the attribute belongs to (function, device): set per context, not per process (a second engine on another device
+  // in the same process would otherwise launch with the 48 KB default)
+  auto key = (const void*)point_tc_kernel<kMode, kVar, kCorr>;
+  if (!c->attr_done.count(key)) {
+    DISN_CUDA_OK(cudaFuncSetAttribute(point_tc_kernel<kMode, kVar, kCorr>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    c->attr_done.insert(key);
   }
   unsigned long long* dbg = nullptr;
   int expt = 0;
@@ -566,8 +586,8 @@ int launch_var(disn_ctx* c, const PointJob& job, const SmallParams& sp, const vo
     expt = getenv("DISN_TC_EXPT") ? atoi(getenv("DISN_TC_EXPT")) : 0;
     DISN_CUDA_OK(cudaMalloc(&dbg, (size_t)pairs * 2 * sizeof(unsigned long long)));
   }
-  point_tc_kernel<kMode, kVar><<<pairs * 2, NTHREADS, smem, c->stream>>>(job, sp, reinterpret_cast<const uint8_t*>(wpk),
-                                                                        tiles_per_img, dbg, expt);
+  point_tc_kernel<kMode, kVar, kCorr><<<pairs * 2, NTHREADS, smem, c->stream>>>(
+      job, sp, reinterpret_cast<const uint8_t*>(wpk), tiles_per_img, dbg, expt);
   if constexpr ((kVar & 1) != 0) {
     std::vector<unsigned long long> h((size_t)pairs * 2);
     DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -576,8 +596,8 @@ int launch_var(disn_ctx* c, const PointJob& job, const SmallParams& sp, const vo
     double sum = 0, mx = 0;
     for (auto v : h) { sum += (double)v; mx = std::max(mx, (double)v); }
     const double tiles = (double)(tiles_per_img * job.B) / pairs;
-    fprintf(stderr, "[DISN_TC_MEASURE expt=%d] CTA cycles: mean %.0f max %.0f  -> %.1f Kcycles per tile (%.1f tiles per pair)\n",
-            expt, sum / h.size(), mx, sum / h.size() / tiles / 1000.0, tiles);
+    fprintf(stderr, "[DISN_TC_MEASURE expt=%d corr=0x%02x] CTA cycles: mean %.0f max %.0f  -> %.1f Kcycles per tile (%.1f tiles per pair)\n",
+            expt, kCorr, sum / h.size(), mx, sum / h.size() / tiles / 1000.0, tiles);
   }
   return 0;
 }
@@ -714,11 +734,23 @@ int launch_point_tc(disn_ctx* c, const PointJob& job_in) {
   if (total == 0) return 0;
   const int pairs = (int)std::min<int64_t>(total, c->num_sms / 2);
   const bool measure = getenv("DISN_TC_MEASURE") != nullptr;
-  int rc;
-  if (measure) rc = f8 ? launch_var<MODE_F16F8, 1>(c, job, sp, wpk, pairs, smem, tiles_per_img)
-                       : launch_var<MODE_BF16X3, 1>(c, job, sp, wpk, pairs, smem, tiles_per_img);
-  else rc = f8 ? launch_var<MODE_F16F8, 0>(c, job, sp, wpk, pairs, smem, tiles_per_img)
-               : launch_var<MODE_BF16X3, 0>(c, job, sp, wpk, pairs, smem, tiles_per_img);
+  int corr = CORR_DEFAULT;
+  if (const char* e = getenv("DISN_TC_CORR")) corr = (int)strtol(e, nullptr, 0);      // A/B: 0xFF = every correction
+  int rc = -2;
+  if (!f8) rc = measure ? launch_var<MODE_BF16X3, 1, 0xFF>(c, job, sp, wpk, pairs, smem, tiles_per_img)
+                        : launch_var<MODE_BF16X3, 0, 0xFF>(c, job, sp, wpk, pairs, smem, tiles_per_img);
+  else {
+    switch (corr) {
+#define DISN_CORR(m)                                                                                  \
+  case m:                                                                                             \
+    rc = measure ? launch_var<MODE_F16F8, 1, m>(c, job, sp, wpk, pairs, smem, tiles_per_img)           \
+                 : launch_var<MODE_F16F8, 0, m>(c, job, sp, wpk, pairs, smem, tiles_per_img);          \
+    break;
+      DISN_CORR(0xFF) DISN_CORR(0xDF)
+#undef DISN_CORR
+      default: DISN_REQUIRE(false, "DISN_TC_CORR: only 0xFF (all corrections) and 0xDF (default) are built");
+    }
+  }
   if (rc) return rc;
   c->launches++;
   DISN_CUDA_OK(cudaGetLastError());

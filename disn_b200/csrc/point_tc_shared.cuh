@@ -49,11 +49,12 @@ constexpr int W8_TILE = 8192;    // 128 rows x 64 k x 1 B (SW64)
 // write one thread's 32 consecutive K values of row p into an A-tile slot.
 // MODE_BF16X3: x0 = bf16 hi tile, x1 = bf16 lo tile (both SW128).
 // MODE_F16F8 : x0 = fp16 tile (SW128), x1 = [e5m2((a-h).sc_lo) | e5m2(a.sc_hi)] two SW64 byte tiles.
+// `res` / `copy`: which of the two e5m2 tiles the consuming layer uses (a layer may drop one or both corrections).
 // MODE_F16F8 also folds the slice's fp16 values into `amax` (all values are post-ReLU, i.e. >= 0): an activation above
 // fp16's 65504 becomes +inf there, which the kernel reports through PointJob::status instead of producing a silent inf.
 template <int kMode>
 __device__ __forceinline__ void store_slice(uint8_t* x0, uint8_t* x1, int p, int h, const float* v, float sc_lo,
-                                            float sc_hi, __half2& amax) {
+                                            float sc_hi, __half2& amax, bool res = true, bool copy = true) {
   if constexpr (kMode == MODE_BF16X3) {
     uint32_t hi[16], lo[16];
 #pragma unroll
@@ -73,12 +74,22 @@ __device__ __forceinline__ void store_slice(uint8_t* x0, uint8_t* x1, int p, int
       const __half2 hh = __floats2half2_rn(a, b);
       amax = __hmax2(amax, hh);
       m[j] = *reinterpret_cast<const uint32_t*>(&hh);
-      const float ra = a - __low2float(hh), rb = b - __high2float(hh);
-      const uint32_t l = __nv_cvt_float2_to_fp8x2(make_float2(ra * sc_lo, rb * sc_lo), __NV_SATFINITE, __NV_E5M2);
-      const __half2 hs = __hmul2(hh, sc_hi2);      // power-of-two scale: exact up to fp16 underflow (below e5m2 precision)
-      const uint32_t g = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hs), __NV_SATFINITE, __NV_E5M2);
-      if (j & 1) { lo[j >> 1] |= l << 16; hi[j >> 1] |= g << 16; }
-      else { lo[j >> 1] = l; hi[j >> 1] = g; }
+      if (res) {     // e5m2 of the fp16 rounding residual (first correction's A operand)
+        const float ra = a - __low2float(hh), rb = b - __high2float(hh);
+        const uint32_t l = __nv_cvt_float2_to_fp8x2(make_float2(ra * sc_lo, rb * sc_lo), __NV_SATFINITE, __NV_E5M2);
+        if (j & 1) lo[j >> 1] |= l << 16;
+        else lo[j >> 1] = l;
+      }
+    }
+    if (copy) {      // e5m2 copy of a (second correction's A operand); skipped for a layer that drops that correction
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const __half2 hh = *reinterpret_cast<const __half2*>(&m[j]);
+        const __half2 hs = __hmul2(hh, sc_hi2);    // power-of-two scale: exact up to fp16 underflow (below e5m2 precision)
+        const uint32_t g = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hs), __NV_SATFINITE, __NV_E5M2);
+        if (j & 1) hi[j >> 1] |= g << 16;
+        else hi[j >> 1] = g;
+      }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -87,8 +98,8 @@ __device__ __forceinline__ void store_slice(uint8_t* x0, uint8_t* x1, int p, int
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const uint32_t off = tc::sw64_offset((uint32_t)p, (uint32_t)(h * 2 + q));
-      *reinterpret_cast<uint4*>(x1 + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-      *reinterpret_cast<uint4*>(x1 + X8_TILE + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+      if (res) *reinterpret_cast<uint4*>(x1 + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+      if (copy) *reinterpret_cast<uint4*>(x1 + X8_TILE + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
     }
   }
 }

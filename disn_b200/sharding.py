@@ -2,8 +2,8 @@
 
 Every query point is independent given the image, so the (z,y,x) grid -- x fastest, z slowest, i.e. slabs
 are contiguous in the output array -- is cut into contiguous z-ranges, one per rank.  No data-path
-collective is needed until the slabs are gathered; uneven slabs are padded to the largest one for
-``all_gather_into_tensor`` and trimmed on unpack.
+collective is needed until the slabs are gathered to rank 0 (``dist.gather`` of slabs padded to the largest
+one, trimmed on unpack); for a host result every rank writes its slab straight into one shared pinned host grid.
 """
 from __future__ import annotations
 
@@ -32,4 +32,12 @@ def unpack_gathered(full, R: int, world: int, out):
     for r in range(world):
         n = b[r + 1] - b[r]
         out[b[r]:b[r + 1]] = full[r * mp:r * mp + n]
+    return out
+
+
+def unpack_gather_list(gathered, R: int, world: int, out):
+    """gathered: list of `world` padded slabs [max_planes, R, R] (dist.gather on rank 0) -> out[R,R,R]."""
+    b = z_bounds(R, world)
+    for r in range(world):
+        out[b[r]:b[r + 1]] = gathered[r][:b[r + 1] - b[r]]
     return out

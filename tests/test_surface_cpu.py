@@ -100,9 +100,23 @@ def _gloo_worker(rank, world, R, port, outdir):
     full = torch.empty((world * mp, R, R))
     dist.all_gather_into_tensor(full, slab)
     out = sharding.unpack_gathered(full, R, world, torch.empty((R, R, R)))
+    # the bench's device path: gather (not all-gather) of the padded slabs to rank 0
+    glist = [torch.empty_like(slab) for _ in range(world)] if rank == 0 else None
+    dist.gather(slab, gather_list=glist, dst=0)
+    # the bench's host path: every rank writes its slab into ONE shared host grid (file-backed shared memory)
+    shm = os.path.join(outdir, "shared_grid.bin")
+    if rank == 0:
+        with open(shm, "wb") as f:
+            f.truncate(R ** 3 * 4)
+    dist.barrier()
+    host = torch.from_file(shm, shared=True, size=R ** 3, dtype=torch.float32).view(R, R, R)
+    host[z0:z1] = slab[:z1 - z0]
+    dist.barrier()
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)                      # the bench's max-over-ranks timing reduction
     if rank == 0:
+        np.save(os.path.join(outdir, "gathered.npy"), sharding.unpack_gather_list(glist, R, world, torch.empty((R, R, R))).numpy())
+        np.save(os.path.join(outdir, "shared.npy"), host.numpy().copy())
         np.save(os.path.join(outdir, "full.npy"), out.numpy())
         np.save(os.path.join(outdir, "tmax.npy"), t.numpy())
     dist.destroy_process_group()
@@ -115,6 +129,8 @@ def test_two_rank_slab_gather_gloo(R, tmp_path):
     mp.spawn(_gloo_worker, args=(2, R, port, str(tmp_path)), nprocs=2, join=True)
     full = np.load(tmp_path / "full.npy")
     np.testing.assert_array_equal(full.reshape(-1), np.arange(R ** 3, dtype=np.float32))
+    np.testing.assert_array_equal(np.load(tmp_path / "gathered.npy"), full)
+    np.testing.assert_array_equal(np.load(tmp_path / "shared.npy"), full)
     assert np.load(tmp_path / "tmax.npy")[0] == 2.0
 
 
