@@ -539,6 +539,42 @@ int disn_eval_grid_resident(disn_ctx* c, const double* sdf_params, const float* 
   return 0;
 }
 
+// ---- cross-process device buffers (multi-GPU gather without a collective) -------------------------------------------
+// Rank 0 allocates the whole-grid buffer and exports a CUDA IPC handle; the other ranks (one process per GPU) open it and
+// pass `ptr + slab offset` as the DISN_DEVICE_PTR output of disn_eval_grid, so the kernel's epilogue stores every
+// SDF value straight into rank 0's HBM over NVLink (peer stores) while it computes: compute and gather are one kernel.
+int disn_shared_alloc(disn_ctx* c, int64_t bytes, void** dev_ptr, unsigned char* handle64) {
+  DISN_REQUIRE(c && dev_ptr && handle64 && bytes > 0, "bad shared_alloc arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  void* p = nullptr;
+  DISN_CUDA_OK(cudaMalloc(&p, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); set_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); return -1; }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+
+int disn_shared_open(disn_ctx* c, const unsigned char* handle64, void** dev_ptr) {
+  DISN_REQUIRE(c && handle64 && dev_ptr, "bad shared_open arguments");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  DISN_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int disn_shared_close(disn_ctx* c, void* dev_ptr, int32_t owner) {
+  DISN_REQUIRE(c && dev_ptr, "bad shared_close arguments");
+  DISN_CUDA_OK(cudaSetDevice(c->cfg.device));
+  DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (owner) DISN_CUDA_OK(cudaFree(dev_ptr));
+  else DISN_CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+
 int disn_fetch(disn_ctx* c, const void* dev, void* host, int64_t bytes) {
   DISN_REQUIRE(c && dev && host && bytes >= 0, "bad fetch arguments");
   DISN_CUDA_OK(cudaSetDevice(c->cfg.device));

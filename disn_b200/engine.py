@@ -267,6 +267,22 @@ class Engine:
         check(self.lib.disn_fetch(self._h, C.c_void_p(dev_ptr), out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
+    # -- cross-process device buffer (peer-store gather) --------------------------------------------
+    def shared_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte IPC handle): rank 0's whole-grid buffer the other ranks' kernels store into."""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        check(self.lib.disn_shared_alloc(self._h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), handle.raw
+
+    def shared_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        check(self.lib.disn_shared_open(self._h, C.create_string_buffer(handle, 64), C.byref(ptr)))
+        return int(ptr.value)
+
+    def shared_close(self, ptr: int, owner: bool):
+        check(self.lib.disn_shared_close(self._h, C.c_void_p(ptr), int(owner)))
+
     def iou(self, verts1, faces1, verts2, faces2, dim: int = 110, want_grids: bool = False):
         """test/test_iou.py:208-233 iou_pymesh on two triangle meshes -> IoU (and the two occupancy grids)."""
         v1, v2 = _f32(verts1), _f32(verts2)

@@ -145,6 +145,15 @@ int disn_cam_estimate(disn_ctx* ctx, const float* imgs, int32_t B, int32_t H, in
 int disn_nn_distance(disn_ctx* ctx, const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M,
                      float* dist1, int32_t* idx1, float* dist2, int32_t* idx2);
 
+/* Multi-GPU result gather without a collective (one process per GPU, SURVEY.md 8e "peer-direct stores from the kernel
+ * epilogue into the root's buffer"): rank 0 calls disn_shared_alloc (cudaMalloc + CUDA IPC handle, 64 bytes), ships the
+ * handle to the other ranks, which disn_shared_open it and pass `ptr + byte offset of their z-slab` as the
+ * DISN_DEVICE_PTR output of disn_eval_grid: the fused kernel then writes each SDF value over NVLink into rank 0's HBM.
+ * disn_shared_close: owner = 1 frees (rank 0), owner = 0 unmaps (the others). */
+int disn_shared_alloc(disn_ctx* ctx, int64_t bytes, void** dev_ptr, unsigned char* handle64);
+int disn_shared_open(disn_ctx* ctx, const unsigned char* handle64, void** dev_ptr);
+int disn_shared_close(disn_ctx* ctx, void* dev_ptr, int32_t owner);
+
 /* IoU evaluator of the reference (test/test_iou.py:208-233 iou_pymesh): both triangle meshes (host float32 verts
  * [nv,3], int32 0-based faces [nf,3]) are voxelised at cell 2/dim (restated pymesh.VoxelGrid: a cell centred at k*cell is
  * occupied iff it overlaps a triangle), the corners of the occupied cells are binned with ((v+1.1)/2.4*dim) truncated, and
