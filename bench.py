@@ -93,6 +93,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        if not self.rows:       # region shorter than one sampling period: take one sample now
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=10).stdout
+                self.rows = [[c.strip() for c in line.split(",")] for line in o.splitlines() if line.strip()]
+            except Exception:
+                pass
         sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
