@@ -8,8 +8,8 @@
 // (the reference runs VGG in fp32; models/CNN/vgg.py:187-196, models/model_normalization.py:76).
 //
 // One CTA = one SM: UMMA M=128 (pixels) x N=128 (output channels) x K=16, 64-wide K slices.
-//   warps 8-15  A producers (two groups of 4 warps alternate slices): thread = one pixel row; gathers 64
-//               channels of one filter tap (256 contiguous bytes, or zeros outside the image), splits to
+//   warps 8-15  A producers (two groups of 4 warps alternate slices): a half-warp gathers the 64 channels of one
+//               filter tap of one pixel row (256 contiguous bytes, coalesced; zeros outside the image), splits to
 //               bf16 hi/lo and writes the K-major 128B-swizzled A tile
 //   warp 0      B producer: host-packed [W_hi | W_lo] 32 KB stage images via cp.async.bulk
 //   warp 1      MMA issuer (warp-uniform loop, elected lane), two TMEM accumulators (ping-pong across jobs)
@@ -181,57 +181,66 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
     }
   } else if (warp >= 8) {
     // ===================== A producers: two groups of 4 warps, alternating slices =====================
+    // Warp w of a group owns rows [32w, 32w+32) of the tile.  Loads are COALESCED: in iteration j a half-warp reads the 256
+    // contiguous bytes (64 channels of one filter tap) of one row -- lane l takes float4 (l & 15) of row 32w + 2j + (l >> 4)
+    // -- so one LDG.128 touches 4 lines instead of 32 (round 1 gave every thread its own row: 8x the L1 wavefronts, which
+    // held the tensor pipe at ~25 %).  A lane converts its 4 values to bf16 hi / lo and stores the two 8-byte half chunks.
     const int grp = (warp - 8) >> 2;                 // 0 / 1
-    const int row = ((warp - 8) & 3) * 32 + lane;    // pixel row of the tile
+    const int w4 = (warp - 8) & 3;
+    const int half = lane >> 4, f4 = lane & 15;      // row parity within the iteration, float4 index within the row
     uint32_t seq = 0;                                // global slice counter (all jobs)
     for (int jj = 0; jj < my_jobs; ++jj) {
       int mt, nb, sp;
       decode((int)blockIdx.x + jj * (int)gridDim.x, mt, nb, sp);
-      const int m = mt * 128 + row;
-      int py = 0, px = 0;
-      const float* img = job.A;
-      if (job.H > 0) {
-        const int hw = job.H * job.W;
-        const int b = m / hw, r = m % hw;
-        py = r / job.W; px = r % job.W;
-        img = job.A + (size_t)b * hw * job.Cin;
+      // per job: the 16 rows this lane touches -> pixel index of the row's own pixel (or the matrix row) and its packed
+      // (y << 16 | x) coordinates; -1 = row beyond M
+      int rpix[16], ryx[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int m = mt * 128 + w4 * 32 + 2 * j + half;
+        rpix[j] = -1; ryx[j] = 0;
+        if (m < job.M) {
+          rpix[j] = m;
+          if (job.H > 0) {
+            const int r = m % (job.H * job.W);
+            ryx[j] = ((r / job.W) << 16) | (r % job.W);
+          }
+        }
       }
       for (int t = 0; t < nsl; ++t, ++seq) {
         if ((int)(seq & 1u) != grp) continue;                  // odd / even slices belong to the two groups
         const int slot = (int)(seq & 3u);                        // the consumer walks the ring in slice order
         const uint32_t use = seq >> 2;                           // uses of this slot so far
         const int k0 = (sp * nsl + t) * 64;
-        const float* src = nullptr;
-        if (m < job.M) {
-          if (job.H > 0) {
-            const int tap = k0 / job.Cin, ci = k0 % job.Cin;
-            const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-            if (yy >= 0 && yy < job.H && xx >= 0 && xx < job.W) src = img + ((size_t)yy * job.W + xx) * job.Cin + ci;
-          } else {
-            src = job.A + (size_t)m * job.K + k0;
-          }
-        }
+        int dy = 0, dx = 0, ci = 0;
+        if (job.H > 0) { const int tap = k0 / job.Cin; ci = k0 % job.Cin; dy = tap / 3 - 1; dx = tap % 3 - 1; }
         float4 v[16];
-        if (src) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 16; ++j) {
+          const float* src = nullptr;
+          if (rpix[j] >= 0) {
+            if (job.H > 0) {
+              const int yy = (ryx[j] >> 16) + dy, xx = (ryx[j] & 0xFFFF) + dx;
+              if (yy >= 0 && yy < job.H && xx >= 0 && xx < job.W)
+                src = job.A + ((size_t)(rpix[j] + dy * job.W + dx)) * job.Cin + ci;
+            } else {
+              src = job.A + (size_t)rpix[j] * job.K + k0;
+            }
+          }
+          v[j] = src ? __ldg(reinterpret_cast<const float4*>(src) + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tc::mbar_wait(&s.aempty[slot], (use & 1) ^ 1);
         uint8_t* ahi = s.a[slot][0];
         uint8_t* alo = s.a[slot][1];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {                            // 8 chunks of 8 bf16 (16 B)
-          uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-          tc::split_bf16x2(v[2 * c].x, v[2 * c].y, h0, l0);
-          tc::split_bf16x2(v[2 * c].z, v[2 * c].w, h1, l1);
-          tc::split_bf16x2(v[2 * c + 1].x, v[2 * c + 1].y, h2, l2);
-          tc::split_bf16x2(v[2 * c + 1].z, v[2 * c + 1].w, h3, l3);
-          const uint32_t off = tc::sw128_offset((uint32_t)row, (uint32_t)c);
-          *reinterpret_cast<uint4*>(ahi + off) = make_uint4(h0, h1, h2, h3);
-          *reinterpret_cast<uint4*>(alo + off) = make_uint4(l0, l1, l2, l3);
+        for (int j = 0; j < 16; ++j) {
+          uint32_t h0, h1, l0, l1;
+          tc::split_bf16x2(v[j].x, v[j].y, h0, l0);
+          tc::split_bf16x2(v[j].z, v[j].w, h1, l1);
+          const uint32_t row = (uint32_t)(w4 * 32 + 2 * j + half);
+          const uint32_t off = tc::sw128_offset(row, (uint32_t)(f4 >> 1)) + (uint32_t)(f4 & 1) * 8u;
+          *reinterpret_cast<uint2*>(ahi + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(alo + off) = make_uint2(l0, l1);
         }
         tc::fence_proxy_async_smem();
         __syncwarp();
