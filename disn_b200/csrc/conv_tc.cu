@@ -181,20 +181,22 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
     }
   } else if (warp >= 8) {
     // ===================== A producers: two groups of 4 warps, alternating slices =====================
-    // Warp w of a group owns rows [32w, 32w+32) of the tile.  Loads are COALESCED: in iteration j a half-warp reads the 256
-    // contiguous bytes (64 channels of one filter tap) of one row -- lane l takes float4 (l & 15) of row 32w + 2j + (l >> 4)
-    // -- so one LDG.128 touches 4 lines instead of 32 (round 1 gave every thread its own row: 8x the L1 wavefronts, which
-    // held the tensor pipe at ~25 %).  A lane converts its 4 values to bf16 hi / lo and stores the two 8-byte half chunks.
+    // Warp w of a group owns rows [32w, 32w+32) of the tile.  Loads are coalesced: in iteration j a half-warp reads the 256
+    // contiguous bytes (64 channels of one filter tap) of one row -- lane l takes float4 (l & 15) of row 32w + 2j + (l >> 4).
+    // The producers are latency bound (ncu: they sit on the first use of the loaded values), so the loop is software
+    // pipelined in half-slices of 8 row pairs: while one half is converted to bf16 hi / lo and stored, the next half's 8
+    // loads (the next slice's, possibly the next job's) are already in flight.
     const int grp = (warp - 8) >> 2;                 // 0 / 1
     const int w4 = (warp - 8) & 3;
     const int half = lane >> 4, f4 = lane & 15;      // row parity within the iteration, float4 index within the row
-    uint32_t seq = 0;                                // global slice counter (all jobs)
-    for (int jj = 0; jj < my_jobs; ++jj) {
+    // iterator over this group's slices (global slice counter parity == grp), across jobs
+    int it_jj = 0, it_t = -1, it_sp = 0;
+    uint32_t it_seq = 0xFFFFFFFFu;
+    int rpix[16], ryx[16];                           // rows of the iterator's current job: pixel index / (y << 16 | x)
+    auto load_job = [&](int jj) {
       int mt, nb, sp;
       decode((int)blockIdx.x + jj * (int)gridDim.x, mt, nb, sp);
-      // per job: the 16 rows this lane touches -> pixel index of the row's own pixel (or the matrix row) and its packed
-      // (y << 16 | x) coordinates; -1 = row beyond M
-      int rpix[16], ryx[16];
+      it_sp = sp;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int m = mt * 128 + w4 * 32 + 2 * j + half;
@@ -207,45 +209,66 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
           }
         }
       }
-      for (int t = 0; t < nsl; ++t, ++seq) {
-        if ((int)(seq & 1u) != grp) continue;                  // odd / even slices belong to the two groups
-        const int slot = (int)(seq & 3u);                        // the consumer walks the ring in slice order
-        const uint32_t use = seq >> 2;                           // uses of this slot so far
-        const int k0 = (sp * nsl + t) * 64;
-        int dy = 0, dx = 0, ci = 0;
-        if (job.H > 0) { const int tap = k0 / job.Cin; ci = k0 % job.Cin; dy = tap / 3 - 1; dx = tap % 3 - 1; }
-        float4 v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float* src = nullptr;
-          if (rpix[j] >= 0) {
-            if (job.H > 0) {
-              const int yy = (ryx[j] >> 16) + dy, xx = (ryx[j] & 0xFFFF) + dx;
-              if (yy >= 0 && yy < job.H && xx >= 0 && xx < job.W)
-                src = job.A + ((size_t)(rpix[j] + dy * job.W + dx)) * job.Cin + ci;
-            } else {
-              src = job.A + (size_t)rpix[j] * job.K + k0;
-            }
-          }
-          v[j] = src ? __ldg(reinterpret_cast<const float4*>(src) + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        tc::mbar_wait(&s.aempty[slot], (use & 1) ^ 1);
-        uint8_t* ahi = s.a[slot][0];
-        uint8_t* alo = s.a[slot][1];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          uint32_t h0, h1, l0, l1;
-          tc::split_bf16x2(v[j].x, v[j].y, h0, l0);
-          tc::split_bf16x2(v[j].z, v[j].w, h1, l1);
-          const uint32_t row = (uint32_t)(w4 * 32 + 2 * j + half);
-          const uint32_t off = tc::sw128_offset(row, (uint32_t)(f4 >> 1)) + (uint32_t)(f4 & 1) * 8u;
-          *reinterpret_cast<uint2*>(ahi + off) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(alo + off) = make_uint2(l0, l1);
-        }
-        tc::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&s.afull[slot]);
+    };
+    // advance to the next slice of this group; false when the work is exhausted
+    auto advance = [&]() -> bool {
+      while (true) {
+        if (it_jj >= my_jobs) return false;
+        ++it_t; ++it_seq;
+        if (it_t >= nsl) { it_t = 0; ++it_jj; if (it_jj >= my_jobs) return false; load_job(it_jj); }
+        if ((int)(it_seq & 1u) == grp) return true;
       }
+    };
+    auto issue = [&](float4* v, int b) {             // loads of half-slice b (row pairs 8b .. 8b+7) of the iterator's slice
+      const int k0 = (it_sp * nsl + it_t) * 64;
+      int dy = 0, dx = 0, ci = 0;
+      if (job.H > 0) { const int tap = k0 / job.Cin; ci = k0 % job.Cin; dy = tap / 3 - 1; dx = tap % 3 - 1; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = 8 * b + i;
+        const float* src = nullptr;
+        if (rpix[j] >= 0) {
+          if (job.H > 0) {
+            const int yy = (ryx[j] >> 16) + dy, xx = (ryx[j] & 0xFFFF) + dx;
+            if (yy >= 0 && yy < job.H && xx >= 0 && xx < job.W)
+              src = job.A + ((size_t)(rpix[j] + dy * job.W + dx)) * job.Cin + ci;
+          } else {
+            src = job.A + (size_t)rpix[j] * job.K + k0;
+          }
+        }
+        v[i] = src ? __ldg(reinterpret_cast<const float4*>(src) + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store = [&](const float4* v, int b, int slot) {
+      uint8_t* ahi = s.a[slot][0];
+      uint8_t* alo = s.a[slot][1];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t h0, h1, l0, l1;
+        tc::split_bf16x2(v[i].x, v[i].y, h0, l0);
+        tc::split_bf16x2(v[i].z, v[i].w, h1, l1);
+        const uint32_t row = (uint32_t)(w4 * 32 + 2 * (8 * b + i) + half);
+        const uint32_t off = tc::sw128_offset(row, (uint32_t)(f4 >> 1)) + (uint32_t)(f4 & 1) * 8u;
+        *reinterpret_cast<uint2*>(ahi + off) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(alo + off) = make_uint2(l0, l1);
+      }
+    };
+    float4 va[8], vb[8];
+    bool have = false;
+    if (my_jobs > 0) { load_job(0); have = advance(); }
+    if (have) issue(va, 0);
+    while (have) {
+      const uint32_t seq = it_seq;                   // the slice whose first half sits in `va`
+      const int slot = (int)(seq & 3u);              // the consumer walks the ring in slice order
+      issue(vb, 1);
+      tc::mbar_wait(&s.aempty[slot], ((seq >> 2) & 1) ^ 1);
+      store(va, 0, slot);
+      have = advance();                              // may switch rpix / ryx to the next job: stores do not need them
+      if (have) issue(va, 0);
+      store(vb, 1, slot);
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.afull[slot]);
     }
   }
   tc::tc_fence_before_sync();
