@@ -41,6 +41,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include <cuda_fp16.h>
@@ -112,6 +113,18 @@ __device__ __forceinline__ uint32_t ring_seq(int sn, int kind, int t, int nstrea
 //             correction saves its MMAs, its 8 KB weight tile per stage (not copied) and its e5m2 A tile (not produced by
 //             the epilogue).  0xFF = every correction (2 bf16-rate units per product); the shipped mask is CORR_DEFAULT.
 #define WAIT(bar, par) tc::mbar_wait(bar, par)
+// measurement build: cycles this thread spends blocked, by barrier class (see the report in launch_var)
+#define TWAIT(cls, bar, par)                                           \
+  do {                                                                 \
+    if constexpr ((kVar & 1) != 0) {                                   \
+      const long long _t = clock64();                                  \
+      tc::mbar_wait(bar, par);                                         \
+      wt[cls] += (unsigned long long)(clock64() - _t);                 \
+    } else {                                                           \
+      tc::mbar_wait(bar, par);                                         \
+    }                                                                  \
+  } while (0)
+enum { W_WEMPTY = 0, W_RELAY, W_ACC5, W_XFULL, W_WFULL, W_PFULL, W_XEMPTY, W_ACCFULL, W_GFULL, W_GEMPTY, W_NCLS };
 // tensor layer of a weight stage from its position in the per-tile consumption cycle
 //   G.L1 0..7 | G.L2 8..23 | L.L0 24 | G.L3 25..32 | L.L1 33..40 | L.L2 41..56 | G.L0 57 | L.L3 58..65
 __host__ __device__ constexpr int stage_layer(uint32_t r) {
@@ -160,6 +173,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
   tc::tc_fence_after_sync();
   const uint32_t tmem = s.tmem_base;
   const long long t_start = (kVar & 1) ? clock64() : 0;
+  unsigned long long wt[W_NCLS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // measurement build only
 
   if (warp == 0 || warp == 2) {
     // ===================== weight producers: warp 0 = even stages (slots 0, 2), warp 2 = odd stages (slots 1, 3) ==========
@@ -167,7 +181,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
     if (lane < 2) {          // two lanes issue one 16 KB tile each so the copies overlap
       for (uint32_t g = pw; g < total_stages; g += 2) {
         const uint32_t slot = g % NW, use = g / NW;
-        WAIT(&s.wempty[slot], (use & 1) ^ 1);
+        TWAIT(W_WEMPTY, &s.wempty[slot], (use & 1) ^ 1);
         uint32_t img_stage;
         int issuer;
         stage_info(g, my_tiles, img_stage, issuer);
@@ -176,11 +190,13 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
         // lane 0: the main tile; lane 1: the e5m2 tiles of the corrections this layer keeps ([e5m2 w | e5m2 residual of w])
         const int sl = stage_layer(img_stage);
         const bool k1 = keep1(sl), k2 = keep2(sl);
-        if (lane == 0) tc::bulk_g2s(s.w[slot], src, W_TILE, bar);
+        // measurement build, expt bit 3: copy a quarter of every tile (results invalid) -- is the kernel L2-bandwidth bound?
+        const uint32_t shr = ((kVar & 1) && (expt & 8)) ? 2u : 0u;
+        if (lane == 0) tc::bulk_g2s(s.w[slot], src, W_TILE >> shr, bar);
         else if (k1 || k2)
-          tc::bulk_g2s(s.w[slot] + W_TILE + (k1 ? 0 : W8_TILE), src + (k1 ? 0 : W8_TILE), (k1 && k2) ? W_TILE : W8_TILE, bar);
+          tc::bulk_g2s(s.w[slot] + W_TILE + (k1 ? 0 : W8_TILE), src + (k1 ? 0 : W8_TILE), ((k1 && k2) ? W_TILE : W8_TILE) >> shr, bar);
         // the byte count may be posted after the copies: the phase cannot complete before this arrival
-        if (lane == 0) tc::mbar_arrive_expect_tx(bar, W_TILE + (k1 ? W8_TILE : 0) + (k2 ? W8_TILE : 0));
+        if (lane == 0) tc::mbar_arrive_expect_tx(bar, (W_TILE + (k1 ? W8_TILE : 0) + (k2 ? W8_TILE : 0)) >> shr);
         __syncwarp(0x3);
       }
     }
@@ -192,7 +208,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
         uint32_t img_stage;
         int issuer;
         stage_info(g, my_tiles, img_stage, issuer);
-        WAIT(&s.wfull[0][slot], (g / NW) & 1);
+        TWAIT(W_RELAY, &s.wfull[0][slot], (g / NW) & 1);
         tc::mbar_arrive_cluster(&s.wfull[issuer][slot], 0);
       }
     }
@@ -220,13 +236,13 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
           const int nnb = (layer == 1 || layer == 2) ? 2 : 1;
           const uint32_t colbase = acc_col(layer, sidx);
           if (layer == 2 && sn > 0) {        // acc4 overwrites the columns the previous stream's acc5 used
-            WAIT(&s.acc5_free, (uint32_t)(sn - 1) & 1);
+            TWAIT(W_ACC5, &s.acc5_free, (uint32_t)(sn - 1) & 1);
             tc::tc_fence_after_sync();
           }
 #pragma unroll 1
           for (int t = 0; t < nsl; ++t) {
             const uint32_t slot = xsl;
-            WAIT(&s.xfull[slot], xph);
+            TWAIT(W_XFULL, &s.xfull[slot], xph);
             tc::tc_fence_after_sync();
             const uint32_t a_hi = x_lo0 + slot * ((2 * X_HALF) >> 4);
             const uint32_t a_lo = a_hi + (X_HALF >> 4);
@@ -234,7 +250,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
             const bool mine = (nnb == 2) || which == 0;
             if (mine) {
               const uint32_t st = (g + (uint32_t)nb) % NW;
-              WAIT(&s.wfull[which][st], wuse[st] & 1);
+              TWAIT(W_WFULL, &s.wfull[which][st], wuse[st] & 1);
               ++wuse[st];
               tc::tc_fence_after_sync();
               const uint32_t d = tmem + colbase + (uint32_t)nb * 128u;
@@ -301,7 +317,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
       const int tile = sn >> 1, sx = sn & 1;
       const uint32_t seq = ring_seq(sn, 2, 0, nstreams);
       const int slot = (int)(seq % NX);
-      WAIT(&s.pfull[tile & 1], (uint32_t)(tile >> 1) & 1);
+      TWAIT(W_PFULL, &s.pfull[tile & 1], (uint32_t)(tile >> 1) & 1);
       const float x = s.px[tile & 1][p], y = s.py[tile & 1][p], z = s.pz[tile & 1][p];
       float v[32];
 #pragma unroll
@@ -313,7 +329,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
         a = fmaf(z, sp.v[sx][SB_W1 + 128 + f], a);
         v[j] = fmaxf(a, 0.f);
       }
-      WAIT(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
+      TWAIT(W_XEMPTY, &s.xempty[slot], ((seq / NX) & 1) ^ 1);
       store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, job.act_scale[sx][0][0], job.act_scale[sx][0][1], amax, keep1(0), keep2(0));
       arrive_xfull(slot);
     };
@@ -323,7 +339,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
                      float sc_hi, uint64_t* accbar, uint32_t accpar, int next_layer) {
       const int slot = (int)(seq % NX);
       if (accbar) {
-        WAIT(accbar, accpar);
+        TWAIT(W_ACCFULL, accbar, accpar);
         tc::tc_fence_after_sync();
       }
       uint32_t r[32];
@@ -342,7 +358,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
       }
       const int gs = t & (NG - 1);           // gather slice t lives in ring slot t % NG (= this group's parity)
       if (gather) {
-        WAIT(&s.gfull[gs], gseq & 1);
+        TWAIT(W_GFULL, &s.gfull[gs], gseq & 1);
         const float* gp = s.g[gs] + (h * 32) * G_LD + p;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += gp[j * G_LD];
@@ -351,7 +367,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
       tc::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + v[j], 0.f);
-      WAIT(&s.xempty[slot], ((seq / NX) & 1) ^ 1);
+      TWAIT(W_XEMPTY, &s.xempty[slot], ((seq / NX) & 1) ^ 1);
       store_slice<kMode>(s.x[slot][0], s.x[slot][1], p, h, v, sc_lo, sc_hi, amax, keep1(next_layer), keep2(next_layer));
       arrive_xfull(slot);
       if (gather && lane == 0) tc::mbar_arrive(&s.gempty[gs]);
@@ -382,7 +398,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
               job.act_scale[sidx][3][1], t == eg ? &s.acc_full[2][0] : (t == eg + 4 ? &s.acc_full[2][1] : nullptr), par, 3);
       if (sn + 1 < nstreams) drain_x3(sn + 1);
       // fold2/conv2 output (256) -> ReLU -> fold2/conv5 dot product
-      WAIT(&s.acc_full[3][0], par);
+      TWAIT(W_ACCFULL, &s.acc_full[3][0], par);
       tc::tc_fence_after_sync();
       float part = 0.f;
       for (int t = 2 * eg; t < 2 * eg + 2; ++t) {
@@ -515,7 +531,7 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
         const uint32_t gsq = (uint32_t)it * 8 + t;
         const int gs = gsq % NG;
         if (pf && t + 1 < 8) prefetch_slice(t + 1);
-        WAIT(&s.gempty[gs], ((gsq / NG) & 1) ^ 1);
+        TWAIT(W_GEMPTY, &s.gempty[gs], ((gsq / NG) & 1) ^ 1);
         float* gdst = s.g[gs];
 #pragma unroll
         for (int i2 = 0; i2 < 4; i2 += 2) {       // two point groups at a time: 16 x 16 B loads in flight per lane
@@ -559,7 +575,13 @@ point_tc_kernel(PointJob job, const __grid_constant__ SmallParams sp, const uint
   // ---- teardown ----
   tc::tc_fence_before_sync();
   tc::cluster_sync();
-  if ((kVar & 1) && dbg && threadIdx.x == 0) dbg[blockIdx.x] = (unsigned long long)(clock64() - t_start);
+  if ((kVar & 1) && dbg) {
+    if (threadIdx.x == 0) dbg[blockIdx.x] = (unsigned long long)(clock64() - t_start);
+    if (lane == 0) {
+      unsigned long long* o = dbg + gridDim.x + ((size_t)blockIdx.x * 16 + warp) * W_NCLS;
+      for (int k = 0; k < W_NCLS; ++k) o[k] = wt[k];
+    }
+  }
   if (warp == 2) tc::tmem_dealloc_cg2(tmem, 512);
 }
 
@@ -584,20 +606,36 @@ int launch_var(disn_ctx* c, const PointJob& job, const SmallParams& sp, const vo
   int expt = 0;
   if constexpr ((kVar & 1) != 0) {
     expt = getenv("DISN_TC_EXPT") ? atoi(getenv("DISN_TC_EXPT")) : 0;
-    DISN_CUDA_OK(cudaMalloc(&dbg, (size_t)pairs * 2 * sizeof(unsigned long long)));
+    DISN_CUDA_OK(cudaMalloc(&dbg, (size_t)pairs * 2 * (1 + 16 * W_NCLS) * sizeof(unsigned long long)));
+    DISN_CUDA_OK(cudaMemsetAsync(dbg, 0, (size_t)pairs * 2 * (1 + 16 * W_NCLS) * sizeof(unsigned long long), c->stream));
   }
   point_tc_kernel<kMode, kVar, kCorr><<<pairs * 2, NTHREADS, smem, c->stream>>>(
       job, sp, reinterpret_cast<const uint8_t*>(wpk), tiles_per_img, dbg, expt);
   if constexpr ((kVar & 1) != 0) {
-    std::vector<unsigned long long> h((size_t)pairs * 2);
+    std::vector<unsigned long long> h((size_t)pairs * 2 * (1 + 16 * W_NCLS));
     DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
     DISN_CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     cudaFree(dbg);
+    const int nc = pairs * 2;
     double sum = 0, mx = 0;
-    for (auto v : h) { sum += (double)v; mx = std::max(mx, (double)v); }
+    for (int i = 0; i < nc; ++i) { sum += (double)h[i]; mx = std::max(mx, (double)h[i]); }
     const double tiles = (double)(tiles_per_img * job.B) / pairs;
     fprintf(stderr, "[DISN_TC_MEASURE expt=%d corr=0x%02x] CTA cycles: mean %.0f max %.0f  -> %.1f Kcycles per tile (%.1f tiles per pair)\n",
-            expt, kCorr, sum / h.size(), mx, sum / h.size() / tiles / 1000.0, tiles);
+            expt, kCorr, sum / nc, mx, sum / nc / tiles / 1000.0, tiles);
+    // blocked cycles per tile by role and barrier class (leader CTAs: even blocks; peer CTAs: odd blocks)
+    static const char* cls[W_NCLS] = {"wempty", "relay", "acc5", "xfull", "wfull", "pfull", "xempty", "accfull", "gfull", "gempty"};
+    static const char* role[16] = {"prod0", "issuer0/relay", "prod1", "issuer1", "epi0.q0", "epi0.q1", "epi0.q2", "epi0.q3", "epi1.q0",
+                                   "epi1.q1", "epi1.q2", "epi1.q3", "front0", "front1", "front2", "front3"};
+    for (int ctak = 0; ctak < 2; ++ctak)
+      for (int w = 0; w < 16; ++w) {
+        double acc[W_NCLS] = {0};
+        for (int p = 0; p < pairs; ++p)
+          for (int k = 0; k < W_NCLS; ++k) acc[k] += (double)h[(size_t)nc + ((size_t)(2 * p + ctak) * 16 + w) * W_NCLS + k] / pairs / tiles;
+        std::string line;
+        for (int k = 0; k < W_NCLS; ++k)
+          if (acc[k] >= 50.0) { char b[64]; snprintf(b, sizeof b, " %s=%.0f", cls[k], acc[k]); line += b; }
+        if (!line.empty()) fprintf(stderr, "[DISN_TC_MEASURE]   %s %-14s blocked cycles/tile:%s\n", ctak ? "peer  " : "leader", role[w], line.c_str());
+      }
   }
   return 0;
 }
