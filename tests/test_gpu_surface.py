@@ -164,3 +164,42 @@ def test_iou_matches_cpu_twin(dim):
         assert eng.iou(a[0], a[1], far[0], far[1], dim=dim) == 0.0
     finally:
         eng.close()
+
+
+def test_pinned_host_outputs_are_written_by_the_kernel(he_weights):
+    """Caller-pinned output buffers (cudaHostAlloc / torch pin_memory) take the zero-copy path -- the kernel's epilogue stores
+    into them directly -- and must give the same bits as pageable buffers (device scratch + copy)."""
+    import torch
+    from disn_b200.engine import Engine
+    eng = Engine(device=0, precision="f16f8", max_batch=2)
+    try:
+        eng.load_weights(he_weights)
+        eng.encode(synth.synthetic_images(2, seed=9))
+        tm = synth.synthetic_trans_mats(2, seed=3)
+        sp = np.tile(synth.DEMO_SDF_PARAMS, (2, 1))
+        ref = eng.eval_grid(sp, tm, 24)                                   # pageable numpy output
+        pinned = torch.empty(ref.shape, dtype=torch.float32).pin_memory()
+        pinned.fill_(float("nan"))
+        out = eng.eval_grid(sp, tm, 24, out=pinned.numpy())
+        assert out.ctypes.data == pinned.data_ptr()
+        np.testing.assert_array_equal(pinned.numpy(), ref)
+        # a z-slab into the middle of a pinned whole-grid buffer (what each rank does in the multi-GPU host path)
+        eng.encode(synth.synthetic_images(1, seed=9))
+        whole = eng.eval_grid(sp[:1], tm[:1], 24)
+        pinned.fill_(float("nan"))
+        eng.eval_grid(sp[:1], tm[:1], 24, z0=5, z1=17, out=pinned.numpy()[0, 5:17].reshape(1, 12, 25, 25))
+        np.testing.assert_array_equal(pinned.numpy()[0, 5:17], whole[0, 5:17])
+        assert np.isnan(pinned.numpy()[0, :5]).all() and np.isnan(pinned.numpy()[0, 17:]).all()
+        eng.encode(synth.synthetic_images(2, seed=9))
+        pts = np.random.default_rng(1).uniform(-1, 1, size=(2, 777, 3)).astype(np.float32)
+        ref_p, ref_uv = eng.eval_points(pts, tm, want_uv=True)
+        import ctypes as C
+        from disn_b200._lib import check
+        pp = torch.empty((2, 777, 1), dtype=torch.float32).pin_memory()
+        puv = torch.empty((2, 777, 2), dtype=torch.float32).pin_memory()
+        check(eng.lib.disn_eval_points(eng._h, pts.ctypes.data_as(C.c_void_p), None, np.ascontiguousarray(tm).ctypes.data_as(C.c_void_p),
+                                       2, 777, C.c_void_p(pp.data_ptr()), C.c_void_p(puv.data_ptr()), 0))
+        np.testing.assert_array_equal(pp.numpy(), ref_p)
+        np.testing.assert_array_equal(puv.numpy(), ref_uv)
+    finally:
+        eng.close()

@@ -92,7 +92,7 @@ def test_round2_candidate_is_faster_in_the_model():
 
 
 def test_v2_static_maps_agree_with_the_issue_order():
-    """point_tc_v2.cu's stage_info() (stage -> image position, consuming issuer) and ring_seq() (activation slice -> ring
+    """point_tc.cu's stage_info() (stage -> image position, consuming issuer) and ring_seq() (activation slice -> ring
     position), restated here, against the MMA issue order and tc_pack_weights' kCyclePos -- incl. the last tile, which has no
     'next stream' entry."""
     FIRST_L0_POS, SPS = 57, 33

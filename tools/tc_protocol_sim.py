@@ -15,8 +15,9 @@ One CTA of the pair is modelled (arrival counts that come from both CTAs are hal
 
 It doubles as a coarse performance model: the operation costs in PARAMS start from the ones measured on B200 (DESIGN.md
 4.1: op-cost probe, wait traces, one-tile timeline) and are tuned so that the model reproduces the measured cycles per tile
-and blocked-time split of the shipped kernel within ~10 % (f16f8: 58.7 K vs 59.9 K measured; bf16x3: see --mode), `report()` prints cycles per tile and the per-agent blocked time in the
-same classes as DISN_TC_TRACE, and `--set key=value` / `--mode` explore what-ifs (ring depths, operand mode, faster
+and blocked-time split of ROUND 1's kernel within ~10 % (f16f8: 58.7 K vs 59.9 K measured; the shipped round-2 kernel is the
+variant --set x2_in_ring=1 --set NW=4 --set issuers=2 --set split_wfull=1, measured at 54.3 K), `report()` prints cycles per tile and
+the per-agent blocked time in the same classes as the DISN_TC_MEASURE build, and `--set key=value` / `--mode` explore what-ifs (ring depths, operand mode, faster
 epilogue ...) before spending GPU time on them.
 
     python tools/tc_protocol_sim.py [--tiles N] [--schedules N] [--mode f16f8|bf16x3] [--set key=value ...] [--report]
