@@ -16,6 +16,8 @@
 //   warps 4-7   epilogue: TMEM -> +bias, ReLU -> fp32 NHWC store (or raw split-K partials to the workspace)
 // Jobs = (m-tile, n-block, k-split); a persistent grid walks them.  Under-filled layers are split along K and
 // reduced by splitk_reduce_kernel.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -56,7 +58,22 @@ struct ConvTcJob {
   int m_tiles, n_blocks, splits, slices_per_split;
 };
 
-__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
+// kMeasure: every warp's lane 0 accounts the cycles it spends blocked on each barrier class (DISN_CONV_MEASURE=1)
+enum { CW_BEMPTY = 0, CW_ACCFREE, CW_AFULL, CW_BFULL, CW_ACCFULL, CW_AEMPTY, CW_NCLS };
+template <bool kMeasure>
+__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job, unsigned long long* __restrict__ dbg) {
+  unsigned long long wt[CW_NCLS] = {0, 0, 0, 0, 0, 0};
+  const long long t_start = kMeasure ? clock64() : 0;
+#define CWAIT(cls, bar, par)                                         \
+  do {                                                               \
+    if constexpr (kMeasure) {                                        \
+      const long long _t = clock64();                                \
+      tc::mbar_wait(bar, par);                                       \
+      wt[cls] += (unsigned long long)(clock64() - _t);               \
+    } else {                                                         \
+      tc::mbar_wait(bar, par);                                       \
+    }                                                                \
+  } while (0)
   extern __shared__ uint8_t smem_raw[];
   ConvTcSmem& s = *reinterpret_cast<ConvTcSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,7 +114,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
         const uint8_t* src = job.wpk + ((size_t)nb * (job.K / 64) + (size_t)sp * nsl) * CT_B_STAGE;
         for (int t = 0; t < nsl; ++t, ++seq) {
           const int st = seq % CT_NB;
-          tc::mbar_wait(&s.bempty[st], ((seq / CT_NB) & 1) ^ 1);
+          CWAIT(CW_BEMPTY, &s.bempty[st], ((seq / CT_NB) & 1) ^ 1);
           tc::mbar_arrive_expect_tx(&s.bfull[st], CT_B_STAGE);
           tc::bulk_g2s(s.b[st], src + (size_t)t * CT_B_STAGE, CT_B_STAGE, &s.bfull[st]);
         }
@@ -112,13 +129,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
     for (int jj = 0; jj < my_jobs; ++jj) {
       const int buf = jj & 1;
       if (jj >= 2) {      // the epilogue must have drained this accumulator (job jj-2)
-        tc::mbar_wait(&s.acc_free[buf], ((jj >> 1) - 1) & 1);
+        CWAIT(CW_ACCFREE, &s.acc_free[buf], ((jj >> 1) - 1) & 1);
         tc::tc_fence_after_sync();
       }
       const uint32_t d = tmem + (uint32_t)buf * 128u;
       for (int t = 0; t < nsl; ++t) {
-        tc::mbar_wait(&s.afull[ast], aph);
-        tc::mbar_wait(&s.bfull[bst], bph);
+        CWAIT(CW_AFULL, &s.afull[ast], aph);
+        CWAIT(CW_BFULL, &s.bfull[bst], bph);
         tc::tc_fence_after_sync();
         const uint32_t a_hi = a_lo0 + ast * ((2 * CT_A_HALF) >> 4), a_lo = a_hi + (CT_A_HALF >> 4);
         const uint32_t b_hi = b_lo0 + bst * (CT_B_STAGE >> 4), b_lo = b_hi + (CT_B_TILE >> 4);
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
       int mt, nb, sp;
       decode((int)blockIdx.x + jj * (int)gridDim.x, mt, nb, sp);
       const int buf = jj & 1;
-      tc::mbar_wait(&s.acc_full[buf], (jj >> 1) & 1);
+      CWAIT(CW_ACCFULL, &s.acc_full[buf], (jj >> 1) & 1);
       tc::tc_fence_after_sync();
       const int m = mt * 128 + row;
       const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * 128u;
@@ -192,20 +209,36 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
     // iterator over this group's slices (global slice counter parity == grp), across jobs
     int it_jj = 0, it_t = -1, it_sp = 0;
     uint32_t it_seq = 0xFFFFFFFFu;
-    int rpix[16], ryx[16];                           // rows of the iterator's current job: pixel index / (y << 16 | x)
+    // rows of the iterator's current job: element offset of the row's own pixel (or matrix row) -- the per-slice part of the
+    // address (tap offset, channel block) is the same for every row -- and, for the im2col view, a 9-bit mask per row of
+    // the filter taps that fall inside the image (3 rows per word).  Round 1 recomputed coordinates, bounds and a 64-bit
+    // product per load: ~40 instructions per LDG.128, which made the producers instruction bound.
+    int64_t rbase[16];
+    uint32_t rmask[6];
     auto load_job = [&](int jj) {
       int mt, nb, sp;
       decode((int)blockIdx.x + jj * (int)gridDim.x, mt, nb, sp);
       it_sp = sp;
 #pragma unroll
+      for (int k = 0; k < 6; ++k) rmask[k] = 0u;
+#pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int m = mt * 128 + w4 * 32 + 2 * j + half;
-        rpix[j] = -1; ryx[j] = 0;
+        rbase[j] = -1;
         if (m < job.M) {
-          rpix[j] = m;
           if (job.H > 0) {
             const int r = m % (job.H * job.W);
-            ryx[j] = ((r / job.W) << 16) | (r % job.W);
+            const int y = r / job.W, x = r % job.W;
+            rbase[j] = (int64_t)m * job.Cin;
+            uint32_t mk = 0u;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+              if (yy >= 0 && yy < job.H && xx >= 0 && xx < job.W) mk |= 1u << tap;
+            }
+            rmask[j / 3] |= mk << (9 * (j % 3));
+          } else {
+            rbase[j] = (int64_t)m * job.K;
           }
         }
       }
@@ -221,22 +254,20 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
     };
     auto issue = [&](float4* v, int b) {             // loads of half-slice b (row pairs 8b .. 8b+7) of the iterator's slice
       const int k0 = (it_sp * nsl + it_t) * 64;
-      int dy = 0, dx = 0, ci = 0;
-      if (job.H > 0) { const int tap = k0 / job.Cin; ci = k0 % job.Cin; dy = tap / 3 - 1; dx = tap % 3 - 1; }
+      int tap = 0;
+      int64_t soff = k0;                             // plain matrix: column offset
+      if (job.H > 0) {
+        tap = k0 / job.Cin;
+        soff = (int64_t)((tap / 3 - 1) * job.W + (tap % 3 - 1)) * job.Cin + (k0 % job.Cin);
+      }
+      const float4* base = reinterpret_cast<const float4*>(job.A + soff) + f4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int j = 8 * b + i;
-        const float* src = nullptr;
-        if (rpix[j] >= 0) {
-          if (job.H > 0) {
-            const int yy = (ryx[j] >> 16) + dy, xx = (ryx[j] & 0xFFFF) + dx;
-            if (yy >= 0 && yy < job.H && xx >= 0 && xx < job.W)
-              src = job.A + ((size_t)(rpix[j] + dy * job.W + dx)) * job.Cin + ci;
-          } else {
-            src = job.A + (size_t)rpix[j] * job.K + k0;
-          }
-        }
-        v[i] = src ? __ldg(reinterpret_cast<const float4*>(src) + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool ok = rbase[j] >= 0;
+        if (job.H > 0) ok = ok && ((rmask[j / 3] >> (9 * (j % 3) + tap)) & 1u);
+        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + rbase[j]))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     auto store = [&](const float4* v, int b, int slot) {
@@ -261,7 +292,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
       const uint32_t seq = it_seq;                   // the slice whose first half sits in `va`
       const int slot = (int)(seq & 3u);              // the consumer walks the ring in slice order
       issue(vb, 1);
-      tc::mbar_wait(&s.aempty[slot], ((seq >> 2) & 1) ^ 1);
+      CWAIT(CW_AEMPTY, &s.aempty[slot], ((seq >> 2) & 1) ^ 1);
       store(va, 0, slot);
       have = advance();                              // may switch rpix / ryx to the next job: stores do not need them
       if (have) issue(va, 0);
@@ -271,9 +302,17 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job) {
       if (lane == 0) tc::mbar_arrive(&s.afull[slot]);
     }
   }
+  if constexpr (kMeasure) {
+    if (lane == 0 && dbg) {
+      unsigned long long* o = dbg + ((size_t)blockIdx.x * 16 + warp) * (CW_NCLS + 1);
+      for (int k = 0; k < CW_NCLS; ++k) o[k] = wt[k];
+      o[CW_NCLS] = (unsigned long long)(clock64() - t_start);
+    }
+  }
   tc::tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc_cg1(tmem, 256);
+#undef CWAIT
 }
 
 }  // namespace
@@ -311,7 +350,8 @@ int launch_conv_tc(disn_ctx* c, const float* A, const uint8_t* wpk, const float*
   DISN_REQUIRE(K % 64 == 0 && N % 32 == 0 && (H == 0 || Cin % 64 == 0), "conv_tc: K%64, N%32, Cin%64");
   const int smem = (int)sizeof(ConvTcSmem) + 1024;
   if (!c->attr_conv_tc) {    // per context (= per device): the attribute is a property of the function ON a device
-    DISN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DISN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DISN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     c->attr_conv_tc = true;
   }
   const int sms = c->num_sms;
@@ -332,7 +372,38 @@ int launch_conv_tc(disn_ctx* c, const float* A, const uint8_t* wpk, const float*
   job.slices_per_split = slices / splits;
   job.ws = splits > 1 ? ws : nullptr;
   const int total = tiles * splits;
-  conv_tc_kernel<<<std::min(total, sms), CT_THREADS, smem, c->stream>>>(job);
+  const int grid = std::min(total, sms);
+  static const bool measure = getenv("DISN_CONV_MEASURE") != nullptr;
+  if (!measure) {
+    conv_tc_kernel<false><<<grid, CT_THREADS, smem, c->stream>>>(job, nullptr);
+  } else {      // diagnostics: synchronous, prints the per-role blocked time of this launch
+    unsigned long long* dbg = nullptr;
+    const size_t n = (size_t)grid * 16 * (CW_NCLS + 1);
+    DISN_CUDA_OK(cudaMalloc(&dbg, n * sizeof(unsigned long long)));
+    DISN_CUDA_OK(cudaMemsetAsync(dbg, 0, n * sizeof(unsigned long long), c->stream));
+    conv_tc_kernel<true><<<grid, CT_THREADS, smem, c->stream>>>(job, dbg);
+    std::vector<unsigned long long> h(n);
+    DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
+    DISN_CUDA_OK(cudaMemcpy(h.data(), dbg, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    static const char* cls[CW_NCLS] = {"bempty", "accfree", "afull", "bfull", "accfull", "aempty"};
+    static const int show[5] = {0, 1, 4, 8, 12};
+    static const char* role[5] = {"Bprod", "MMA", "epi.q0", "Aprod.g0", "Aprod.g1"};
+    double tot = 0;
+    for (int b = 0; b < grid; ++b) tot += (double)h[((size_t)b * 16 + 1) * (CW_NCLS + 1) + CW_NCLS] / grid;
+    fprintf(stderr, "[DISN_CONV_MEASURE] M=%d N=%d K=%d H=%d splits=%d jobs=%d grid=%d: %.0f cycles/CTA, tensor work %.0f cycles/CTA |",
+            M, N, K, H, splits, total, grid, tot, (double)total / grid * job.slices_per_split * 768.0);
+    for (int r = 0; r < 5; ++r) {
+      fprintf(stderr, " %s{", role[r]);
+      for (int k = 0; k < CW_NCLS; ++k) {
+        double a = 0;
+        for (int b = 0; b < grid; ++b) a += (double)h[((size_t)b * 16 + show[r]) * (CW_NCLS + 1) + k] / grid;
+        if (a >= 0.02 * tot) fprintf(stderr, "%s=%.0f%% ", cls[k], 100.0 * a / tot);
+      }
+      fprintf(stderr, "}");
+    }
+    fprintf(stderr, "\n");
+  }
   c->launches++;
   DISN_CUDA_OK(cudaGetLastError());
   *splits_out = splits;
