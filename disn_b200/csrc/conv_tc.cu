@@ -16,6 +16,7 @@
 //   warps 4-7   epilogue: TMEM -> +bias, ReLU -> fp32 NHWC store (or raw split-K partials to the workspace)
 // Jobs = (m-tile, n-block, k-split); a persistent grid walks them.  Under-filled layers are split along K and
 // reduced by splitk_reduce_kernel.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -175,19 +176,17 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(ConvTcJob job, u
         tc::tmem_ld_x32(taddr + c0, r);
         tc::tmem_ld_wait();
         if (m < job.M && nb * 128 + c0 < job.N) {     // N is a multiple of 32; the padded columns are never stored
+          const bool fin = !job.ws;                    // final values (bias, ReLU) or raw split-K partials
+          const float4* bp = (fin && job.bias) ? reinterpret_cast<const float4*>(job.bias + nb * 128 + c0) : nullptr;
+          const float lo = (fin && job.relu) ? 0.f : -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = bp ? __ldg(bp + (j >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 o;
-            float* op = reinterpret_cast<float*>(&o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float v = __uint_as_float(r[j + q]);
-              if (!job.ws) {
-                if (job.bias) v += __ldg(job.bias + nb * 128 + c0 + j + q);
-                if (job.relu) v = fmaxf(v, 0.f);
-              }
-              op[q] = v;
-            }
+            o.x = fmaxf(__uint_as_float(r[j]) + b4.x, lo);
+            o.y = fmaxf(__uint_as_float(r[j + 1]) + b4.y, lo);
+            o.z = fmaxf(__uint_as_float(r[j + 2]) + b4.z, lo);
+            o.w = fmaxf(__uint_as_float(r[j + 3]) + b4.w, lo);
             *reinterpret_cast<float4*>(dst + c0 + j) = o;
           }
         }

@@ -634,8 +634,22 @@ static int encoder_body(disn_ctx* c, int B, int H, int W, int C, bool embedding_
   PmapLevels lv;
   for (int l = 0; l < 5; ++l) {
     int hw = kTapHW[l];
+    const float* src = c->taps[l];
+    if (hw > c->cfg.img_h && c->cfg.img_h == c->cfg.img_w) {
+      // resize and projection commute (both linear per channel): where the tap is LARGER than the 137x137 target (conv1_2,
+      // 224x224) resize first -- the GEMM then has 2.7x fewer rows and the [B,224,224,512] intermediate (103 MB per image)
+      // never exists.  This is also the reference's own order (model_normalization.py:171-172).
+      float* tmp = c->act[0];
+      const int oh = c->cfg.img_h;
+      const int64_t total = (int64_t)B * oh * oh * kTapC[l];
+      resize_bilinear_tf_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, c->stream>>>(
+          c->taps[l], tmp, B, hw, hw, kTapC[l], oh, oh);
+      c->launches++;
+      src = tmp;
+      hw = oh;
+    }
     ConvGeom g{0, 0, 0};
-    if (gemm_any(c, "proj" + std::to_string(l), A_PLAIN, c->taps[l], wl + (int64_t)off * kHidden, nullptr, c->proj[l],
+    if (gemm_any(c, "proj" + std::to_string(l), A_PLAIN, src, wl + (int64_t)off * kHidden, nullptr, c->proj[l],
                  B * hw * hw, kHidden, kTapC[l], 0, g))
       return -1;
     off += kTapC[l];
