@@ -68,13 +68,15 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index=0, period_ms=100):
+        self.rows, self.proc, self.gpu, self.period_ms = [], None, gpu_index, period_ms
 
     def start(self):
+        if self.period_ms <= 0:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -86,14 +88,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        if not self.rows:       # region shorter than one sampling period: take one sample now
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if not self.rows:       # region shorter than one sampling period (or no background sampler): take one sample now
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=10).stdout
@@ -109,8 +110,10 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w": float(np.median(pw)) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w": float(np.median(pw)) if pw else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -364,7 +367,7 @@ def run_ours(args):
     warm = max(3, args.warmup)
     for _ in range(warm):
         step_device()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_period_ms)
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count
@@ -508,6 +511,8 @@ def main():
     ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
     ap.add_argument("--precision", default=os.environ.get("DISN_PRECISION", "f16f8"), choices=["fp32", "bf16x3", "f16f8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period-ms", type=int, default=100, dest="clock_period_ms",
+                    help="nvidia-smi sampling period during the timed region (0 = one sample right after it)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the z-slabs reach rank 0's HBM (peer = stores from the kernel epilogue over NVLink)")
     args = ap.parse_args()
