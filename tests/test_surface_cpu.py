@@ -239,3 +239,25 @@ def test_tf_checkpoint_reader_against_independently_assembled_bundle(tmp_path):
     open(d0, "wb").write(bytes(flipped))
     with pytest.raises(ValueError, match="crc32c"):
         ck.load_checkpoint(prefix, verify_data=True, model_variables_only=False)
+
+
+def test_bench_contract_helpers():
+    """bench.py: both arms print the same config.workload for every BASELINE config, the clock sampler degrades to a
+    one-shot sample / 'unavailable' without nvidia-smi, and the z-slab bookkeeping of the host path covers the grid."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.workload_string(1) == "single 137x137 image, --sdf_res 256 (257^3 = 16974593 points), twostream, encoder included per step"
+    assert bench.workload_string(0).startswith("single 137x137 image, --sdf_res 64 (65^3 = 274625 points)")
+    assert bench.workload_string(2).startswith("batch of 8 137x137 images, --sdf_res 128 (8 x 129^3 = 17173512 points)")
+    assert bench.workload_string(4).startswith("single 137x137 image, --sdf_res 512 (513^3 = 135005697 points)")
+    assert abs(bench.F_ALG - 2 * 2 * (3 * 64 + 64 * 256 + 256 * 512 + 512 * 512 + 512 * 256 + 256)) < 1e-9
+    s = bench.ClockSampler(0, period_ms=0)
+    s.start()
+    out = s.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    from disn_b200 import sharding
+    for world in (1, 2, 4, 8):
+        b = sharding.z_bounds(257, world)
+        assert sum(b[i + 1] - b[i] for i in range(world)) == 257
