@@ -134,7 +134,6 @@ struct disn_ctx {
   int64_t tc_weights_bytes = 0;
   void* tc_weights_f8 = nullptr;       // fp16 + e5m2 stage images (DISN_PREC_F16F8)
   float tc_act_scale[2][4][2] = {};
-  bool tc_small_ok = false;
   float tc_small[2][2048] = {};         // host copy of the per-stream small parameters (the point kernel's __grid_constant__ table)
   std::map<std::string, uint8_t*> enc_tc_weights;   // packed bf16 hi/lo stage images of the encoder GEMMs
   // marching cubes: persistent scratch + the device-resident mesh of the last run (mc.cu)

@@ -739,7 +739,6 @@ int tc_pack_weights(disn_ctx* c) {
   DISN_CUDA_OK(cudaStreamSynchronize(c->stream));
 
   // host copy of the small per-stream parameters at the SB_* offsets (the kernel's __grid_constant__ parameter table)
-  c->tc_small_ok = true;
   for (int sidx = 0; sidx < 2; ++sidx) {
     const std::string p = sidx ? "sdfprediction_imgfeat" : "sdfprediction";
     const struct { const char* name; int off, n; } small[7] = {

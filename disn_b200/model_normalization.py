@@ -193,6 +193,16 @@ class Session:
             if key != self._img_key:        # the reference re-runs VGG per chunk; once per image is enough
                 self.engine.encode(imgs)
                 self._img_key = key
+        if any(k in ("head_global", "head_local") for k in kinds):      # sdfnet heads on their own (explicit features)
+            from . import sdfnet
+            res = []
+            for f in flist:
+                src = self._feed(feed_dict, f.graph.pl.get("head_src_pc"))
+                feats = self._feed(feed_dict, f.graph.pl.get("head_globalfeats" if f.kind == "head_global" else "head_point_feat"))
+                if src is None or feats is None:
+                    raise ValueError("the head's src_pc / feature placeholders were not fed")
+                res.append(sdfnet.eval_head(self.engine, f.kind, src, feats))
+            return res[0] if single else res
         if "decoder_pred" in kinds:                     # get_decoder graph: explicit features, no encoder
             if len(set(kinds)) != 1:
                 raise ValueError("fetch the decoder output on its own")

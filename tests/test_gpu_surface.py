@@ -50,6 +50,19 @@ def test_intermediates_and_decoder_split_point(he_weights, precision):
                                        feat_pls["point_img_feat"]: pf})
         assert out.shape == (B, N, 1)
         assert np.abs(out - ref["pred_sdf"]).max() / orc.SDF_WEIGHT <= 1e-4
+        # the two sdfnet heads on their own (models/sdfnet.py:69,171): symbolic through Session.run and eager on arrays
+        from disn_b200 import sdfnet
+        hp = model.Placeholder("src_pc", (B, N, 3))
+        hg = model.Placeholder("globalfeats", (B, 1, 1, 1024))
+        hf = model.Placeholder("point_feat", (B, N, 1, 1472))
+        tg = sdfnet.get_sdf_basic2(hp, hg, False, B, N, False, None)
+        tl = sdfnet.get_sdf_basic2_imgfeat_twostream(hp, hf, False, B, N, False, None)
+        og, ol = sess.run([tg, tl], feed_dict={hp: rot, hg: emb, hf: pf})
+        assert np.abs(og - ref["pred_sdf_value_global"]).max() / orc.SDF_WEIGHT <= 1e-4
+        assert np.abs(ol - ref["pred_sdf_value_local"]).max() / orc.SDF_WEIGHT <= 1e-4
+        sdfnet.set_engine(sess.engine)
+        np.testing.assert_array_equal(sdfnet.get_sdf_basic2(rot, emb, False, B, N, False, None), og)
+        sdfnet.set_engine(None)
         # and our own fetched features close the loop: decoder(point_img_feat, embedding) == fused pred_sdf
         out2 = sess.run(dec, feed_dict={pls["sample_pc_rot"]: rot,
                                         feat_pls["ref_feats_embedding_cnn"]: sess.engine.get_encoded(0).reshape(B, 1, 1, 1024),
