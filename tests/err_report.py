@@ -1,5 +1,6 @@
 """Max |sdf - oracle64| of the tensor-core point kernel per precision mode / correction mask on N random points per image
-(2 images).   python tools/err_report.py [N] [--masks 0xFF,0xDF,...]"""
+(2 images).   python tests/err_report.py [N] [--masks 0xFF,0xDF,...]
+Test infrastructure (it calls the oracle as the checker), hence under tests/."""
 import os
 import sys
 
