@@ -78,6 +78,25 @@ def test_config1_res256_grid_vs_oracle_at_sampled_indices(eng8, he_weights, orac
     np.testing.assert_array_equal(np.concatenate(slabs, axis=1), grid)
 
 
+def test_config1_every_point_of_the_grid_vs_the_fp32_path(eng8):
+    """The sampled tests above see 20 000 of the 16 974 593 points.  This one compares EVERY point of the 257^3 grid of the
+    shipped operand mode with the CUDA-core fp32 path of the same library on the same encoder products (the fp32 path is
+    anchored to the float64 oracle at <= 2e-6 by test_gpu_parity.py), so the maximum over the whole grid is bounded too:
+    |f16f8 - oracle| <= |f16f8 - fp32| + |fp32 - oracle| <= 9e-5 + 1e-5."""
+    imgs = synth.synthetic_images(1, seed=1234)
+    tm, sp = synth.DEMO_TRANS_MAT, synth.DEMO_SDF_PARAMS
+    eng8.set_precision("f16f8")
+    eng8.encode(imgs)
+    g_tc = eng8.eval_grid(sp, tm, 256)
+    eng8.set_precision("fp32")
+    g_32 = eng8.eval_grid(sp, tm, 256)
+    eng8.set_precision("f16f8")
+    assert g_tc.shape == g_32.shape == (1, 257, 257, 257)
+    d = np.abs(g_tc.astype(np.float64) - g_32)
+    print("full-grid max |f16f8 - fp32| = %.3e, rms %.3e, max |sdf| %.3f" % (d.max(), np.sqrt((d ** 2).mean()), np.abs(g_32).max()))
+    assert d.max() <= 9e-5, float(d.max())
+
+
 @pytest.mark.parametrize("init", ["he", "xavier"])
 def test_config0_res64_grid_vs_oracle(eng8, he_weights, oracle_enc8, init):
     """BASELINE config 0 (demo.py, --sdf_res 64 -> 65^3 = 274 625 points, 2 chunks of 137 313): f16f8 output vs the
