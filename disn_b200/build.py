@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdisn_b200.so")
 TEST_LIB = os.path.join(HERE, "libdisn_b200_test.so")
 SOURCES = ["api.cu", "encoder.cu", "point_fp32.cu", "point_tc.cu", "mc.cu", "chamfer.cu", "conv_tc.cu", "cam.cu", "iou.cu",
-           "decoder.cu"]
+           "decoder.cu", "emd.cu"]
 # diagnostics: selftests / probes, plus encoder.cu rebuilt with its debug GEMM harness -> libdisn_b200_test.so
 DIAG_SOURCES = ["tc_selftest.cu", "tc_probe.cu"]
 EXTRA_FLAGS = {"iou.cu": ["--fmad=false"]}     # voxel classification must match the float64 oracle operation for operation

@@ -217,6 +217,40 @@ class Engine:
         df, _, db, _ = self.nn_distance(pred, src)
         return (df.mean(axis=1) + db.mean(axis=1)) * np.float32(1000)
 
+    def approx_match(self, xyz1, xyz2, cost=False):
+        """The reference's tf_approxmatch.approx_match(xyz1, xyz2) (models/tf_ops/approxmatch/tf_approxmatch.py:12-20):
+        match [B,N,M] float32, element (k,l) = mass moved from point k of xyz1 to point l of xyz2.  cost=True also returns
+        match_cost(xyz1, xyz2, match) [B] from the same call."""
+        a, b = _f32(xyz1), _f32(xyz2)
+        B, N, _ = a.shape
+        M = b.shape[1]
+        m = np.empty((B, N, M), np.float32)
+        cst = np.empty(B, np.float32) if cost else None
+        check(self.lib.disn_approx_match(self._h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), B, N, M,
+                                         m.ctypes.data_as(C.c_void_p), cst.ctypes.data_as(C.c_void_p) if cost else None))
+        return (m, cst) if cost else m
+
+    def match_cost(self, xyz1, xyz2, match):
+        """tf_approxmatch.match_cost(xyz1, xyz2, match) (tf_approxmatch.py:28-37): cost [B]."""
+        a, b, m = _f32(xyz1), _f32(xyz2), _f32(match)
+        B, N, _ = a.shape
+        M = b.shape[1]
+        assert m.shape == (B, N, M), m.shape
+        cst = np.empty(B, np.float32)
+        check(self.lib.disn_match_cost(self._h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                       m.ctypes.data_as(C.c_void_p), B, N, M, cst.ctypes.data_as(C.c_void_p)))
+        return cst
+
+    def emd(self, src, pred):
+        """test/test_cd_emd.py:307-308: match_cost(src, pred, approx_match(src, pred)) * 0.01 per batch item; the match
+        matrix stays in HBM."""
+        a, b = _f32(src), _f32(pred)
+        B, N, _ = a.shape
+        cst = np.empty(B, np.float32)
+        check(self.lib.disn_approx_match(self._h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), B, N, b.shape[1],
+                                         None, cst.ctypes.data_as(C.c_void_p)))
+        return cst * np.float32(0.01)
+
     def f_score(self, pred, src, thresholds):
         """test/test_f_score.py:231-236: precision / recall = fraction of sqrt NN distances (pred->src / src->pred)
         below each threshold; F = 2PR/(P+R).  pred, src: [1,N,3] / [1,M,3].  Distances come from the CUDA NN kernel."""

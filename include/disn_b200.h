@@ -145,6 +145,17 @@ int disn_cam_estimate(disn_ctx* ctx, const float* imgs, int32_t B, int32_t H, in
 int disn_nn_distance(disn_ctx* ctx, const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M,
                      float* dist1, int32_t* idx1, float* dist2, int32_t* idx2);
 
+/* Approximate earth mover's distance, the reference's ApproxMatch / MatchCost ops (models/tf_ops/approxmatch/
+ * tf_approxmatch.cpp:23-85, 86-107; called at test/test_cd_emd.py:307-308): xyz1 [B,N,3], xyz2 [B,M,3] host float32.
+ * disn_approx_match -> match [B,N,M] float32 (element (k,l): mass moved from point k of xyz1 to point l of xyz2 -- the CPU
+ * op's k*M+l indexing) and/or cost [B] = MatchCost of that match; either output may be NULL (cost only: `match` never leaves
+ * HBM).  disn_match_cost = the MatchCost op for a caller-supplied match.  Same arithmetic as the reference CPU kernels
+ * (float64 sums in a fixed order, expf of a float32 exponent): equal to them within the float64 summation order. */
+int disn_approx_match(disn_ctx* ctx, const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M,
+                      float* match_out, float* cost_out);
+int disn_match_cost(disn_ctx* ctx, const float* xyz1, const float* xyz2, const float* match, int32_t B, int32_t N, int32_t M,
+                    float* cost);
+
 /* Multi-GPU result gather without a collective (one process per GPU, SURVEY.md 8e "peer-direct stores from the kernel
  * epilogue into the root's buffer"): rank 0 calls disn_shared_alloc (cudaMalloc + CUDA IPC handle, 64 bytes), ships the
  * handle to the other ranks, which disn_shared_open it and pass `ptr + byte offset of their z-slab` as the

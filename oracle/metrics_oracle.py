@@ -5,6 +5,10 @@ for each point of set 1 the minimum over set 2 of the float32 value (dx*dx + dy*
 It is PINNED against the reference itself: oracle/_ref/libref_nndistance.so is that file compiled in place
 (oracle/Makefile, stub TF headers in oracle/ref_stubs) and tests/test_oracle_cpu.py compares the two bit for bit.
 Chamfer: test/test_cd_emd.py:300-301; precision/recall/F: test/test_f_score.py:159-186,231-236.
+
+approx_match / match_cost restate models/tf_ops/approxmatch/tf_approxmatch.cpp:23-85 (`approxmatch_cpu`) and :86-107
+(`matchcost_cpu`), the approximate earth mover's distance of test/test_cd_emd.py:307-308; pinned the same way against
+oracle/_ref/libref_approxmatch.so (tests/test_oracle_cpu.py) and through tests/golden/approxmatch_ref.npz on the GPU box.
 """
 import ctypes as C
 import os
@@ -13,6 +17,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_LIB = os.path.join(HERE, "_ref", "libref_nndistance.so")
+REF_AM_LIB = os.path.join(HERE, "_ref", "libref_approxmatch.so")
 
 
 def nn_distance(xyz1, xyz2):
@@ -50,6 +55,90 @@ def ref_nn_distance(xyz1, xyz2):
     if rc:
         raise ValueError(err.value.decode())
     return d1, i1, d2, i2
+
+
+def approx_match(xyz1, xyz2):
+    """tf_approxmatch.cpp:23-85.  xyz1 [B,N,3], xyz2 [B,M,3] float32 -> match [B,N,M] float32 (element (k,l) = mass moved from
+    point k of set 1 to point l of set 2; the op declares the shape (B,M,N) but indexes k*m+l, so for N != M the layout is this).
+    Eleven rounds j = 8..-2 of a soft assignment with weights expf(-4^j d^2) (level 0 in the last round); every point of set 1
+    can give max(N,M)/N units, every point of set 2 can take max(N,M)/M (integer division).  Arithmetic: float32 coordinates
+    widened to float64, the exponent rounded to float32, expf in float32, everything else float64, `match` accumulated
+    in float32."""
+    a = np.ascontiguousarray(xyz1, np.float32).astype(np.float64)
+    b = np.ascontiguousarray(xyz2, np.float32).astype(np.float64)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    out = np.zeros((B, N, M), np.float32)
+    for i in range(B):
+        d2 = ((a[i][:, None, 0] - b[i][None, :, 0]) ** 2 + (a[i][:, None, 1] - b[i][None, :, 1]) ** 2) \
+            + (a[i][:, None, 2] - b[i][None, :, 2]) ** 2
+        satl = np.full(N, float(max(N, M) // N))
+        satr = np.full(M, float(max(N, M) // M))
+        for j in range(8, -3, -1):
+            level = 0.0 if j == -2 else -float(np.float32(4.0) ** np.float32(j))
+            e = np.exp((level * d2).astype(np.float32).astype(np.float64)).astype(np.float32)      # expf of a float32 argument
+            w = e.astype(np.float64) * satr[None, :]
+            s = 1e-9 + w.sum(axis=1)
+            w = w / s[:, None] * satl[:, None]
+            ss = 1e-9 + w.sum(axis=0)
+            w = w * np.minimum(satr / ss, 1.0)[None, :]
+            satl = np.maximum(satl - w.sum(axis=1), 0.0)
+            out[i] = (out[i].astype(np.float64) + w).astype(np.float32)
+            satr = np.maximum(satr - w.sum(axis=0), 0.0)
+    return out
+
+
+def match_cost(xyz1, xyz2, match):
+    """tf_approxmatch.cpp:86-107: cost[b] = sum_kl sqrtf(|p_k - q_l|^2) * match[k,l]; distances and products in float32,
+    the sum in float64, the result stored as float32."""
+    a = np.ascontiguousarray(xyz1, np.float32)
+    b = np.ascontiguousarray(xyz2, np.float32)
+    mt = np.ascontiguousarray(match, np.float32)
+    d = (b[:, None, :, :] - a[:, :, None, :]).astype(np.float32)
+    s = ((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]).astype(np.float32) + d[..., 2] * d[..., 2]).astype(np.float32)
+    t = (np.sqrt(s).astype(np.float32) * mt).astype(np.float32)
+    return t.astype(np.float64).sum(axis=(1, 2)).astype(np.float32)
+
+
+def emd(xyz1, xyz2):
+    """test/test_cd_emd.py:307-308: match_cost(src, pred, approx_match(src, pred)) * 0.01 per batch item."""
+    return match_cost(xyz1, xyz2, approx_match(xyz1, xyz2)) * np.float32(0.01)
+
+
+def _ref_am():
+    if not os.path.exists(REF_AM_LIB):
+        raise FileNotFoundError(REF_AM_LIB)
+    return C.CDLL(REF_AM_LIB)
+
+
+def ref_approx_match(xyz1, xyz2):
+    """The reference's own compiled CPU op (oracle/_ref); raises FileNotFoundError when it was not built."""
+    lib = _ref_am()
+    a = np.ascontiguousarray(xyz1, np.float32)
+    b = np.ascontiguousarray(xyz2, np.float32)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    out = np.empty((B, N, M), np.float32)
+    err = C.create_string_buffer(256)
+    if lib.ref_approx_match(B, N, M, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                            err, 256):
+        raise ValueError(err.value.decode())
+    return out
+
+
+def ref_match_cost(xyz1, xyz2, match):
+    lib = _ref_am()
+    a = np.ascontiguousarray(xyz1, np.float32)
+    b = np.ascontiguousarray(xyz2, np.float32)
+    mt = np.ascontiguousarray(match, np.float32)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    out = np.empty(B, np.float32)
+    err = C.create_string_buffer(256)
+    if lib.ref_match_cost(B, N, M, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), mt.ctypes.data_as(C.c_void_p),
+                          out.ctypes.data_as(C.c_void_p), err, 256):
+        raise ValueError(err.value.decode())
+    return out
 
 
 def chamfer_x1000(pred, src):

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE: a minimal stand-in for the TensorFlow op-kernel API, just enough to compile the
-// reference's models/tf_ops/nn_distance/tf_nndistance.cpp *where it lies* (TensorFlow is not installable here)
-// and run its CPU kernel NnDistanceOp::Compute as the oracle for the Chamfer-distance evaluator.
+// reference's models/tf_ops/nn_distance/tf_nndistance.cpp and models/tf_ops/approxmatch/tf_approxmatch.cpp *where they
+// lie* (TensorFlow is not installable here) and run their CPU kernels (NnDistanceOp, ApproxMatchOp, MatchCostOp ::Compute)
+// as the oracles of the Chamfer-distance and EMD evaluators.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -47,6 +48,8 @@ struct Tensor {
   template <class T> Flat<const T> flat() const { return Flat<const T>{reinterpret_cast<const T*>(buf.data())}; }
 };
 
+template <class T> struct DataTypeToEnum { static constexpr int value = 0; };
+
 struct OpKernelConstruction {};
 struct OpKernelContext {
   std::vector<Tensor> inputs;
@@ -59,6 +62,7 @@ struct OpKernelContext {
     *t = outputs[i];
     return Status::OK();
   }
+  Status allocate_temp(int, const TensorShape& s, Tensor* t) { *t = Tensor(s, 4); return Status::OK(); }
   ~OpKernelContext() { for (auto* t : outputs) delete t; }
 };
 struct OpKernel {

@@ -122,6 +122,51 @@ def test_nn_distance_oracle_matches_reference_compiled_op():
     np.testing.assert_array_equal(i1[0], brute.argmin(1))
 
 
+def _approxmatch_golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "approxmatch_ref.npz"))
+    return g, sorted({k.rsplit("_", 1)[0] for k in g.files})
+
+
+def test_approx_match_oracle_matches_reference_compiled_op():
+    """oracle/metrics_oracle.approx_match / match_cost == the reference's own CPU ops compiled in place (oracle/_ref): equal
+    but for the float64 summation order and the last bit of expf (measured <= 4e-9 absolute on `match`; the bar is 2 ulp of float32
+    at 1.0, since numpy's exp differs in the last bit between SIMD code paths)."""
+    import pytest
+    from oracle import metrics_oracle as mo
+    rng = np.random.default_rng(3)
+    for B, N, M in ((2, 64, 64), (1, 96, 32), (1, 40, 100), (1, 7, 1)):
+        a = rng.uniform(-0.5, 0.5, (B, N, 3)).astype(np.float32)
+        b = rng.uniform(-0.5, 0.5, (B, M, 3)).astype(np.float32)
+        try:
+            ref = mo.ref_approx_match(a, b)
+        except FileNotFoundError:
+            pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+        got = mo.approx_match(a, b)
+        np.testing.assert_allclose(got, ref, rtol=2.5e-7, atol=2.5e-7)
+        np.testing.assert_allclose(mo.match_cost(a, b, ref), mo.ref_match_cost(a, b, ref), rtol=1e-7)
+        # what a point can give / take bounds its row / column mass (tf_approxmatch.cpp:25-27)
+        assert (got.sum(axis=2) <= max(N, M) // N + 1e-5).all() and (got.sum(axis=1) <= max(N, M) // M + 1e-5).all()
+
+
+def test_approx_match_oracle_against_golden_reference_outputs():
+    """The committed outputs of the reference's CPU ops (tests/golden/make_golden_approxmatch.py) -- runs where
+    /root/reference and oracle/_ref do not exist."""
+    from oracle import metrics_oracle as mo
+    g, names = _approxmatch_golden()
+    assert names == ["dups", "same", "single", "square", "tall", "wide"]
+    for n in names:
+        a, b = g[n + "_xyz1"], g[n + "_xyz2"]
+        m = mo.approx_match(a, b)
+        np.testing.assert_allclose(m, g[n + "_match"], rtol=2.5e-7, atol=2.5e-7, err_msg=n)
+        np.testing.assert_allclose(mo.match_cost(a, b, g[n + "_match"]), g[n + "_cost"], rtol=1e-7, atol=1e-12, err_msg=n)
+    # identical clouds: everything stays in place, the distance is ~0 (4e-9 from the 1e-9 regularisers)
+    assert g["same_cost"][0] < 1e-6
+    assert np.allclose(np.diagonal(g["same_match"][0]), 1.0, atol=1e-6)
+    # test/test_cd_emd.py:308
+    np.testing.assert_allclose(mo.emd(g["square_xyz1"], g["square_xyz2"]), g["square_cost"] * np.float32(0.01), rtol=1e-6)
+
+
 def test_rotation_from_ortho6d_is_orthonormal_and_right_handed():
     """models/posenet.py:22-36: columns (x, y, z) orthonormal with z = x × y_raw normalised, det +1."""
     from oracle import disn_oracle as orc
