@@ -251,6 +251,18 @@ class Engine:
                                          None, cst.ctypes.data_as(C.c_void_p)))
         return cst * np.float32(0.01)
 
+    def points_loss(self, sampled_pc):
+        """get_points_loss of test/test_cd_emd.py:291-315: sampled_pc [1+V,N,3] = the ground-truth cloud followed by the
+        clouds of V predicted views.  Returns (avg_cf, min_cf, arg_min_cf, avg_em, min_em, arg_min_em) over the views:
+        Chamfer x1000 and approximate EMD x0.01 of every view against the ground truth."""
+        pc = _f32(sampled_pc)
+        pred = pc[1:]
+        src = np.ascontiguousarray(np.broadcast_to(pc[:1], pred.shape))
+        cf = self.chamfer_x1000(pred, src)
+        em = self.emd(src, pred)
+        return (np.float32(cf.mean()), np.float32(cf.min()), int(cf.argmin()),
+                np.float32(em.mean()), np.float32(em.min()), int(em.argmin()))
+
     def f_score(self, pred, src, thresholds):
         """test/test_f_score.py:231-236: precision / recall = fraction of sqrt NN distances (pred->src / src->pred)
         below each threshold; F = 2PR/(P+R).  pred, src: [1,N,3] / [1,M,3].  Distances come from the CUDA NN kernel."""

@@ -70,3 +70,17 @@ def test_approx_match_ragged_and_errors(engine):
         engine.approx_match(a[:, :0], b)
     with pytest.raises(DisnError):
         engine.match_cost(a, b[:, :0], np.zeros((3, 1, 0), np.float32))
+
+
+def test_points_loss_like_the_evaluation_script(engine):
+    """Engine.points_loss == get_points_loss (test/test_cd_emd.py:291-315) evaluated with the CPU oracles."""
+    rng = np.random.default_rng(13)
+    gt = rng.uniform(-0.5, 0.5, (1, 512, 3)).astype(np.float32)
+    views = np.concatenate([gt + rng.normal(0, s, gt.shape).astype(np.float32) for s in (0.05, 0.01, 0.1)], 0)
+    got = engine.points_loss(np.concatenate([gt, views], 0))
+    src = np.repeat(gt, 3, 0)
+    cf, em = mo.chamfer_x1000(views, src), mo.emd(src, views)
+    want = (cf.mean(), cf.min(), int(cf.argmin()), em.mean(), em.min(), int(em.argmin()))
+    assert got[2] == want[2] == 1 and got[5] == want[5] == 1           # the least noisy view wins both
+    np.testing.assert_allclose([got[0], got[1]], [want[0], want[1]], rtol=1e-6)
+    np.testing.assert_allclose([got[3], got[4]], [want[3], want[4]], rtol=2e-6)
